@@ -1,0 +1,132 @@
+// Shared device/host helpers for the cvxopt_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include "../../include/cvxopt_b200.h"
+
+namespace cvxb {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern unsigned long long g_launches;          // kernels launched by this library
+inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+
+#define CVXB_CUDA(expr)                                                            \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            cvxb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,          \
+                            cudaGetErrorString(_e));                               \
+            return CVXB_E_CUDA;                                                    \
+        }                                                                          \
+    } while (0)
+
+#define CVXB_TRY(expr)                                                             \
+    do {                                                                           \
+        int _r = (expr);                                                           \
+        if (_r != 0) return _r;                                                    \
+    } while (0)
+
+#define CVXB_LAUNCH_CHECK()                                                        \
+    do {                                                                           \
+        cudaError_t _e = cudaGetLastError();                                       \
+        if (_e != cudaSuccess) {                                                   \
+            cvxb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,      \
+                            cudaGetErrorString(_e));                               \
+            return CVXB_E_CUDA;                                                    \
+        }                                                                          \
+    } while (0)
+
+constexpr int kNumSMs = 148;       // B200: 2 dies x 74 SMs
+constexpr int NB = 128;            // Cholesky block size == GEMM tile edge
+
+// ---- device helpers ---------------------------------------------------------
+#ifdef __CUDACC__
+// fp64 tensor-core MMA: D(8x8) += A(8x4,row) * B(4x8,col).  SASS: DMMA.8x8x4.
+// lane -> A[lane>>2][lane&3], B[k=lane&3][n=lane>>2], D[lane>>2][2*(lane&3)+{0,1}]
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+// 16-byte async copy global->shared, zero-filling (16 - src_bytes) trailing bytes.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem),
+                 "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(smem)), "l"(gmem),
+                 "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#endif
+
+// ---- host-side kernels' launch API (device pointers, explicit stream) --------
+struct GemmDesc {
+    // C[r,c] = alpha * sum_k X[r,k] * w[k] * Y[c,k] + beta * D[r,c]      (col-major C/D)
+    // X[r,k] = x_kmajor ? X[k + r*ldx] : X[r + k*ldx]; same for Y.
+    int M = 0, N = 0, K = 0;
+    const double *X = nullptr; int ldx = 0; bool x_kmajor = false;
+    const double *Y = nullptr; int ldy = 0; bool y_kmajor = false;
+    const double *w = nullptr;          // optional K-vector applied inside the contraction
+    const double *D = nullptr; int ldd = 0;
+    double *C = nullptr; int ldc = 0;
+    double alpha = 1.0, beta = 0.0;
+    bool lower_only = false;            // only tiles with r-tile >= c-tile (M == N)
+    // tile-column window (look-ahead in the Cholesky): only c-tiles in [ct_begin, ct_end)
+    int ct_begin = 0, ct_end = 1 << 30;
+    // batching (blockIdx.z): element strides between consecutive problems
+    int batch = 1;
+    long long sX = 0, sY = 0, sW = 0, sD = 0, sC = 0;
+    // split-K remainder workspace (>= kNumSMs * 128*128 doubles) or nullptr to disable
+    double *splitk_ws = nullptr;
+};
+int dmma_gemm(const GemmDesc &g, cudaStream_t st);
+
+// Cholesky (lower) of the n x n matrix A in place; inv receives the inverses of the
+// NB x NB diagonal blocks of L (block j at inv + j*NB*NB, leading dimension NB).
+// info (device int) = first non-positive pivot (1-based) or 0.
+struct CholWork {
+    cudaStream_t panel_stream = nullptr;   // high-priority: diagonal block, panel, next-panel update
+    cudaStream_t update_stream = nullptr;  // low-priority: bulk trailing update
+    cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr, ev_end_p = nullptr,
+                ev_end_u = nullptr;
+    int *d_info = nullptr;                // device flag
+    int *d_flags = nullptr;               // trsv progress flags (>= n/NB + 1 ints)
+    double *splitk_ws = nullptr;
+};
+int chol_work_create(CholWork &w);
+void chol_work_destroy(CholWork &w);
+int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_t st);
+// b := L^{-T} L^{-1} b  (potrs with one right-hand side)
+int potrs_lower(int n, const double *L, int ldl, const double *inv, double *b, CholWork &w,
+                cudaStream_t st);
+int trsv_lower(int n, const double *L, int ldl, const double *inv, double *b, bool trans,
+               CholWork &w, cudaStream_t st);
+
+}  // namespace cvxb

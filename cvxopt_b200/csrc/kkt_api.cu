@@ -1,0 +1,471 @@
+// C ABI of the KKT hot path (see include/cvxopt_b200.h).
+//
+// cvxb_kkt mirrors the closure chain of the reference's misc.kkt_chol
+// (src/python/misc.py:1213-1349):  create == kkt_chol(G, dims, A),
+// factor == factor(W, H, Df), solve == solve(x, y, z).  G (and optionally H) are
+// uploaded once and stay resident in HBM; per factor only the O(cdim) scaling
+// parameters cross PCIe, per solve only the right-hand side / solution.
+#include "cone.cuh"
+#include <cstdarg>
+#include <mutex>
+
+namespace cvxb {
+
+static thread_local std::string g_err;
+unsigned long long g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+static int check_device(int device) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s): cvxopt_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return CVXB_E_NOGPU;
+    }
+    if (device < 0 || device >= cnt) {
+        set_error("device %d out of range (%d visible)", device, cnt);
+        return CVXB_E_ARG;
+    }
+    cudaDeviceProp prop;
+    CVXB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device,
+                  prop.major, prop.minor);
+        return CVXB_E_NOGPU;
+    }
+    CVXB_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+}  // namespace cvxb
+
+using namespace cvxb;
+
+struct cvxb_kkt {
+    int device = 0;
+    int n = 0, p = 0;
+    ConeLayout cone;
+    const double *G = nullptr;   // cdim x n, rows [mnl, cdim) hold G (rows [0,mnl) belong to Df)
+    long long ldg = 0;
+    bool own_G = false;
+    double *Hres = nullptr;      // resident H (symmetrised), or null
+    double *Hbuf = nullptr;      // per-call H upload buffer (lazy)
+    double *Kmat = nullptr;      // n x n: normal equations, then its Cholesky factor (lower)
+    double *inv = nullptr;       // inverses of the diagonal blocks of L
+    double *Gs = nullptr;        // scaled+packed rows that are not 'l': [mnl | q | s packed] x n
+    long long ldgs = 0;
+    int nrest = 0;
+    double *Gunp = nullptr;      // unpacked scaled 's' rows (sums2 x n) — only when ns > 0
+    double *Dfbuf = nullptr;     // mnl x n upload buffer
+    DevScaling W;
+    double *bzp = nullptr, *zin = nullptr, *zt = nullptr, *xv = nullptr, *yv = nullptr;
+    double *gemv_ws = nullptr;
+    double *swork = nullptr;
+    size_t swork_doubles = 0;
+    CholWork cw;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    double factor_ms = 0, solve_ms = 0, br[3] = {0, 0, 0};
+    bool factored = false;
+};
+
+namespace {
+
+int upload_matrix(double *dst, long long ldd, const double *src, long long lds, int rows, int cols,
+                  int space, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return 0;
+    cudaMemcpyKind kind = (space == CVXB_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CVXB_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), src, lds * sizeof(double),
+                                (size_t)rows * sizeof(double), cols, kind, st));
+    return 0;
+}
+
+int xfer_vec(double *dst, const double *src, size_t n, int space, bool to_device, cudaStream_t st) {
+    if (n == 0) return 0;
+    cudaMemcpyKind kind = (space == CVXB_DEVICE) ? cudaMemcpyDeviceToDevice
+                          : (to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+    CVXB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), kind, st));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *cvxb_last_error(void) { return g_err.c_str(); }
+int cvxb_version(void) { return 100; }
+unsigned long long cvxb_launch_count(void) { return g_launches; }
+
+int cvxb_device_count(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < cnt; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int cvxb_malloc(void **dptr, unsigned long long bytes) {
+    CVXB_CUDA(cudaMalloc(dptr, bytes ? bytes : 8));
+    return 0;
+}
+int cvxb_free(void *dptr) { CVXB_CUDA(cudaFree(dptr)); return 0; }
+int cvxb_memcpy_h2d(void *dst, const void *src, unsigned long long bytes) {
+    CVXB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int cvxb_memcpy_d2h(void *dst, const void *src, unsigned long long bytes) {
+    CVXB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int cvxb_sync(void) { CVXB_CUDA(cudaDeviceSynchronize()); return 0; }
+
+// --------------------------------------------------------------------- create
+int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const double *G,
+                    int ldg, const double *A, int lda, int space, int device) {
+    if (!out) { set_error("kkt_create: out is NULL"); return CVXB_E_ARG; }
+    *out = nullptr;
+    if (n < 0 || p < 0) { set_error("kkt_create: negative size"); return CVXB_E_ARG; }
+    if (p > 0) {
+        (void)A; (void)lda;
+        set_error("kkt_create: equality constraints (p > 0) are not built yet");
+        return CVXB_E_UNSUP;
+    }
+    CVXB_TRY(check_device(device));
+    cvxb_kkt *k = new cvxb_kkt();
+    k->device = device; k->n = n; k->p = p;
+    int rc = k->cone.init(dims);
+    if (rc) { delete k; return rc; }
+    const ConeLayout &c = k->cone;
+    if (c.cdim > 0 && (!G || ldg < (c.cdim > 1 ? c.cdim : 1))) {
+        set_error("kkt_create: G must be cdim x n with ldg >= cdim (cdim=%d, ldg=%d)", c.cdim, ldg);
+        cvxb_kkt_destroy(k);
+        return CVXB_E_ARG;
+    }
+    auto fail = [&](int r) { cvxb_kkt_destroy(k); return r; };
+#define KTRY(expr) do { int _r = (expr); if (_r) return fail(_r); } while (0)
+#define KCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+        set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+        return fail(_e == cudaErrorMemoryAllocation ? CVXB_E_NOMEM : CVXB_E_CUDA); } } while (0)
+    KCUDA(cudaStreamCreateWithFlags(&k->st, cudaStreamNonBlocking));
+    KCUDA(cudaEventCreate(&k->e0)); KCUDA(cudaEventCreate(&k->e1));
+    KCUDA(cudaEventCreate(&k->e2)); KCUDA(cudaEventCreate(&k->e3));
+    KTRY(chol_work_create(k->cw));
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    if (space == CVXB_DEVICE) {
+        k->G = G; k->ldg = ldg; k->own_G = false;
+    } else {
+        double *g = nullptr;
+        k->ldg = (c.cdim + 1) & ~1;     // even leading dimension: 16-byte aligned columns
+        if (k->ldg < 2) k->ldg = 2;
+        KCUDA(cudaMalloc(&g, (size_t)k->ldg * nn * sizeof(double)));
+        k->G = g; k->own_G = true;
+        KTRY(upload_matrix(g, k->ldg, G, ldg, c.cdim, n, CVXB_HOST, k->st));
+    }
+    const long long ldk = (n + 1) & ~1;
+    KCUDA(cudaMalloc(&k->Kmat, (size_t)(ldk > 2 ? ldk : 2) * nn * sizeof(double)));
+    const int nblk = (n + NB - 1) / NB + 1;
+    KCUDA(cudaMalloc(&k->inv, (size_t)nblk * NB * NB * sizeof(double)));
+    k->nrest = c.mnl + c.sumq + c.sump;
+    if (k->nrest > 0) {
+        k->ldgs = (k->nrest + 1) & ~1;
+        KCUDA(cudaMalloc(&k->Gs, (size_t)k->ldgs * nn * sizeof(double)));
+    }
+    if (c.sums2 > 0) {
+        KCUDA(cudaMalloc(&k->Gunp, (size_t)c.sums2 * nn * sizeof(double)));
+        // workspace for the congruences: symmetric copies + intermediate, chunked over columns
+        size_t per_col = (size_t)2 * c.maxs * c.maxs;
+        size_t cols = (size_t)n < 1 ? 1 : (size_t)n;
+        size_t want = per_col * cols;
+        const size_t cap = (size_t)1 << 29;            // 4 GiB of doubles at most
+        if (want > cap) want = (cap / per_col ? cap / per_col : 1) * per_col;
+        k->swork_doubles = want;
+        KCUDA(cudaMalloc(&k->swork, want * sizeof(double)));
+    }
+    if (c.mnl > 0) KCUDA(cudaMalloc(&k->Dfbuf, (size_t)c.mnl * nn * sizeof(double)));
+    KTRY(k->W.alloc(c));
+    const size_t cd = (size_t)(c.cdim > 0 ? c.cdim : 1);
+    KCUDA(cudaMalloc(&k->bzp, cd * sizeof(double)));
+    KCUDA(cudaMalloc(&k->zin, cd * sizeof(double)));
+    KCUDA(cudaMalloc(&k->zt, cd * sizeof(double)));
+    KCUDA(cudaMalloc(&k->xv, nn * sizeof(double)));
+    KCUDA(cudaMalloc(&k->yv, (cd > nn ? cd : nn) * sizeof(double)));
+    KCUDA(cudaMalloc(&k->gemv_ws, cd * (size_t)gemv_n_chunks(n) * sizeof(double)));
+    KCUDA(cudaStreamSynchronize(k->st));
+#undef KTRY
+#undef KCUDA
+    *out = k;
+    return 0;
+}
+
+void cvxb_kkt_destroy(cvxb_kkt *k) {
+    if (!k) return;
+    cudaSetDevice(k->device);
+    if (k->st) cudaStreamSynchronize(k->st);
+    if (k->own_G && k->G) cudaFree(const_cast<double *>(k->G));
+    double *bufs[] = {k->Hres, k->Hbuf, k->Kmat, k->inv, k->Gs, k->Gunp, k->Dfbuf, k->bzp,
+                      k->zin, k->zt, k->xv, k->yv, k->gemv_ws, k->swork};
+    for (double *b : bufs) if (b) cudaFree(b);
+    k->W.destroy();
+    k->cone.destroy();
+    chol_work_destroy(k->cw);
+    cudaEvent_t evs[] = {k->e0, k->e1, k->e2, k->e3};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (k->st) cudaStreamDestroy(k->st);
+    delete k;
+}
+
+static long long kkt_ldk(const cvxb_kkt *k) { long long l = (k->n + 1) & ~1; return l > 2 ? l : 2; }
+
+int cvxb_kkt_set_H(cvxb_kkt *k, const double *H, int ldh, int space) {
+    if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
+    CVXB_CUDA(cudaSetDevice(k->device));
+    if (!H) {
+        if (k->Hres) cudaFree(k->Hres);
+        k->Hres = nullptr;
+        return 0;
+    }
+    if (ldh < (k->n > 1 ? k->n : 1)) { set_error("set_H: ldh < n"); return CVXB_E_ARG; }
+    const long long ldk = kkt_ldk(k);
+    if (!k->Hres) CVXB_CUDA(cudaMalloc(&k->Hres, (size_t)ldk * (k->n > 0 ? k->n : 1) * sizeof(double)));
+    CVXB_TRY(upload_matrix(k->Hres, ldk, H, ldh, k->n, k->n, space, k->st));
+    // only tril(H) is significant in the reference (misc.py:1276-1277); make the resident
+    // copy fully symmetric so it also serves the P(x, y) operator
+    CVXB_TRY(symmetrize_lower(k->n, k->Hres, ldk, 1, 0, k->st));
+    CVXB_CUDA(cudaStreamSynchronize(k->st));
+    return 0;
+}
+
+// --------------------------------------------------------------------- factor
+int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ldh,
+                    const double *Df, int lddf, int use_resident_H, int space) {
+    if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
+    CVXB_CUDA(cudaSetDevice(k->device));
+    const ConeLayout &c = k->cone;
+    const int n = k->n;
+    cudaStream_t st = k->st;
+    k->factored = false;
+    const long long ldk = kkt_ldk(k);
+    CVXB_CUDA(cudaEventRecord(k->e0, st));
+    CVXB_TRY(k->W.upload(c, Wp, space, st));
+    const double *Hptr = nullptr;
+    long long ldH = ldk;
+    if (H) {
+        if (ldh < (n > 1 ? n : 1)) { set_error("factor: ldh < n"); return CVXB_E_ARG; }
+        if (space == CVXB_DEVICE) { Hptr = H; ldH = ldh; }
+        else {
+            if (!k->Hbuf) CVXB_CUDA(cudaMalloc(&k->Hbuf, (size_t)ldk * (n > 0 ? n : 1) * sizeof(double)));
+            CVXB_TRY(upload_matrix(k->Hbuf, ldk, H, ldh, n, n, CVXB_HOST, st));
+            Hptr = k->Hbuf;
+        }
+    } else if (use_resident_H && k->Hres) {
+        Hptr = k->Hres;
+    }
+    // ---- Gs rows that cannot be folded into the SYRK operand load: [Df | q | s] ----
+    if (c.mnl > 0) {
+        if (!Df) { set_error("factor: Df is required when mnl > 0"); return CVXB_E_ARG; }
+        const double *Dfd = Df; long long ldd = lddf;
+        if (space != CVXB_DEVICE) {
+            CVXB_TRY(upload_matrix(k->Dfbuf, c.mnl, Df, lddf, c.mnl, n, CVXB_HOST, st));
+            Dfd = k->Dfbuf; ldd = c.mnl;
+        }
+        CVXB_TRY(scale_rows(Dfd, ldd, k->Gs, k->ldgs, c.mnl, n, k->W.dnli, st));
+    }
+    if (c.nq > 0)
+        CVXB_TRY(scale_q(c, k->W, k->G + c.mnl + c.ml, k->ldg, k->Gs + c.mnl, k->ldgs, n, true, st));
+    if (c.ns > 0) {
+        // W^{-T} on an 's' block: rti' * mat(x) * rti  (trans 'T', inverse 'I'), then pack2
+        CVXB_TRY(scale_s(c, k->W, k->G + c.mnl + c.ml + c.sumq, k->ldg, k->Gunp, c.sums2, n, 'T',
+                         'I', k->swork, k->swork_doubles, st));
+        CVXB_TRY(pack_s(c, k->Gunp, c.sums2, k->Gs + c.mnl + c.sumq, k->ldgs, n, false, st));
+    }
+    CVXB_CUDA(cudaEventRecord(k->e1, st));
+    // ---- K = H + G_l' diag(di^2) G_l + Gs' Gs   (lower triangle) ----
+    bool have = false;
+    if (c.ml > 0 && n > 0) {
+        GemmDesc g;
+        g.M = n; g.N = n; g.K = c.ml;
+        g.X = k->G + c.mnl; g.ldx = (int)k->ldg; g.x_kmajor = true;
+        g.Y = g.X; g.ldy = g.ldx; g.y_kmajor = true;
+        g.w = k->W.di2;
+        g.D = Hptr; g.ldd = (int)ldH; g.beta = 1.0;
+        g.C = k->Kmat; g.ldc = (int)ldk;
+        g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
+        CVXB_TRY(dmma_gemm(g, st));
+        have = true;
+    }
+    if (k->nrest > 0 && n > 0) {
+        GemmDesc g;
+        g.M = n; g.N = n; g.K = k->nrest;
+        g.X = k->Gs; g.ldx = (int)k->ldgs; g.x_kmajor = true;
+        g.Y = g.X; g.ldy = g.ldx; g.y_kmajor = true;
+        g.D = have ? k->Kmat : Hptr; g.ldd = have ? (int)ldk : (int)ldH; g.beta = 1.0;
+        g.C = k->Kmat; g.ldc = (int)ldk;
+        g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
+        CVXB_TRY(dmma_gemm(g, st));
+        have = true;
+    }
+    if (!have && n > 0) {
+        if (!Hptr) { set_error("factor: no cone rows and no H: KKT matrix is singular"); return 1; }
+        CVXB_TRY(upload_matrix(k->Kmat, ldk, Hptr, ldH, n, n, CVXB_DEVICE, st));
+    }
+    CVXB_CUDA(cudaEventRecord(k->e2, st));
+    // ---- Cholesky ----
+    CVXB_TRY(potrf_lower(n, k->Kmat, (int)ldk, k->inv, k->cw, st));
+    CVXB_CUDA(cudaEventRecord(k->e3, st));
+    int info = 0;
+    CVXB_CUDA(cudaMemcpyAsync(&info, k->cw.d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CVXB_CUDA(cudaStreamSynchronize(st));
+    float t;
+    cudaEventElapsedTime(&t, k->e0, k->e3); k->factor_ms = t;
+    cudaEventElapsedTime(&t, k->e0, k->e1); k->br[0] = t;
+    cudaEventElapsedTime(&t, k->e1, k->e2); k->br[1] = t;
+    cudaEventElapsedTime(&t, k->e2, k->e3); k->br[2] = t;
+    if (info > 0) {
+        set_error("factor: leading minor of order %d is not positive definite", info);
+        return info;
+    }
+    k->factored = true;
+    return 0;
+}
+
+// --------------------------------------------------------------------- solve
+int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
+    if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
+    if (!k->factored) { set_error("solve called before a successful factor"); return CVXB_E_ARG; }
+    (void)y;   // p == 0
+    CVXB_CUDA(cudaSetDevice(k->device));
+    const ConeLayout &c = k->cone;
+    const int n = k->n;
+    cudaStream_t st = k->st;
+    const long long ldk = kkt_ldk(k);
+    const int nlq = c.mnl + c.ml + c.sumq;     // rows that are identical packed / unpacked
+    CVXB_CUDA(cudaEventRecord(k->e0, st));
+    double *xd = x, *zd = z;
+    if (space != CVXB_DEVICE) {
+        CVXB_TRY(xfer_vec(k->xv, x, n, CVXB_HOST, true, st));
+        CVXB_TRY(xfer_vec(k->zin, z, c.cdim, CVXB_HOST, true, st));
+        xd = k->xv; zd = k->zin;
+    }
+    // bzp := pack(W^{-T} bz)                                   (misc.py:1306-1307)
+    if (c.mnl > 0) CVXB_TRY(scale_rows(zd, c.cdim, k->bzp, c.cdim, c.mnl, 1, k->W.dnli, st));
+    if (c.ml > 0)
+        CVXB_TRY(scale_rows(zd + c.mnl, c.cdim, k->bzp + c.mnl, c.cdim, c.ml, 1, k->W.di, st));
+    if (c.nq > 0)
+        CVXB_TRY(scale_q(c, k->W, zd + c.mnl + c.ml, c.cdim, k->bzp + c.mnl + c.ml, c.cdim, 1, true, st));
+    if (c.ns > 0) {
+        CVXB_TRY(scale_s(c, k->W, zd + nlq, c.cdim, k->zt + nlq, c.cdim, 1, 'T', 'I', k->swork,
+                         k->swork_doubles, st));
+        CVXB_TRY(pack_s(c, k->zt + nlq, c.cdim, k->bzp + nlq, c.cdim, 1, true, st));
+    }
+    // x := x + Gs' bzp                                            (misc.py:1311)
+    if (c.ml > 0)
+        CVXB_TRY(gemv_t(c.ml, n, k->G + c.mnl, k->ldg, k->W.di, k->bzp + c.mnl, 1.0, 1.0, xd, st));
+    if (c.mnl > 0) CVXB_TRY(gemv_t(c.mnl, n, k->Gs, k->ldgs, nullptr, k->bzp, 1.0, 1.0, xd, st));
+    if (k->nrest - c.mnl > 0)
+        CVXB_TRY(gemv_t(k->nrest - c.mnl, n, k->Gs + c.mnl, k->ldgs, nullptr,
+                        k->bzp + c.mnl + c.ml, 1.0, 1.0, xd, st));
+    // x := K^{-1} x                                               (misc.py:1327)
+    CVXB_TRY(potrs_lower(n, k->Kmat, (int)ldk, k->inv, xd, k->cw, st));
+    // bzp := Gs x - bzp                                           (misc.py:1344)
+    if (c.ml > 0)
+        CVXB_TRY(gemv_n(c.ml, n, k->G + c.mnl, k->ldg, k->W.di, xd, 1.0, -1.0, k->bzp + c.mnl,
+                        k->gemv_ws, st));
+    if (c.mnl > 0)
+        CVXB_TRY(gemv_n(c.mnl, n, k->Gs, k->ldgs, nullptr, xd, 1.0, -1.0, k->bzp, k->gemv_ws, st));
+    if (k->nrest - c.mnl > 0)
+        CVXB_TRY(gemv_n(k->nrest - c.mnl, n, k->Gs + c.mnl, k->ldgs, nullptr, xd, 1.0, -1.0,
+                        k->bzp + c.mnl + c.ml, k->gemv_ws, st));
+    // z := unpack(bzp)                                            (misc.py:1345)
+    if (nlq > 0)
+        CVXB_CUDA(cudaMemcpyAsync(zd, k->bzp, (size_t)nlq * sizeof(double),
+                                  cudaMemcpyDeviceToDevice, st));
+    if (c.ns > 0) CVXB_TRY(unpack_s(c, k->bzp + nlq, c.cdim, zd + nlq, c.cdim, 1, st));
+    if (space != CVXB_DEVICE) {
+        CVXB_TRY(xfer_vec(x, k->xv, n, CVXB_HOST, false, st));
+        CVXB_TRY(xfer_vec(z, k->zin, c.cdim, CVXB_HOST, false, st));
+    }
+    CVXB_CUDA(cudaEventRecord(k->e1, st));
+    CVXB_CUDA(cudaStreamSynchronize(st));
+    float t;
+    cudaEventElapsedTime(&t, k->e0, k->e1);
+    k->solve_ms = t;
+    return 0;
+}
+
+int cvxb_kkt_get_L(cvxb_kkt *k, double *L_host, int ldl) {
+    if (!k || !L_host || ldl < k->n) { set_error("get_L: bad arguments"); return CVXB_E_ARG; }
+    CVXB_CUDA(cudaSetDevice(k->device));
+    CVXB_CUDA(cudaMemcpy2D(L_host, (size_t)ldl * sizeof(double), k->Kmat, kkt_ldk(k) * sizeof(double),
+                           (size_t)k->n * sizeof(double), k->n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int cvxb_kkt_last_ms(cvxb_kkt *k, double *factor_ms, double *solve_ms) {
+    if (!k) return CVXB_E_ARG;
+    if (factor_ms) *factor_ms = k->factor_ms;
+    if (solve_ms) *solve_ms = k->solve_ms;
+    return 0;
+}
+int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3) {
+    if (!k || !ms3) return CVXB_E_ARG;
+    ms3[0] = k->br[1]; ms3[1] = k->br[2]; ms3[2] = k->br[0];
+    return 0;
+}
+
+int cvxb_kkt_gemv_G(cvxb_kkt *k, const double *x, double *y, double alpha, double beta, int trans,
+                    int space) {
+    if (!k || !x || !y) { set_error("gemv_G: bad arguments"); return CVXB_E_ARG; }
+    CVXB_CUDA(cudaSetDevice(k->device));
+    const ConeLayout &c = k->cone;
+    const int n = k->n, m = c.cdim - c.mnl;
+    cudaStream_t st = k->st;
+    const double *Gp = k->G + c.mnl;
+    const bool tr = (trans == 'T' || trans == 't');
+    const int nx = tr ? m : n, ny = tr ? n : m;
+    const double *xd = x; double *yd = y;
+    if (space != CVXB_DEVICE) {
+        // zin/yv are cdim long, xv is n long: pick by role
+        double *xb = tr ? k->zin : k->xv, *yb = tr ? k->xv : k->yv;
+        CVXB_TRY(xfer_vec(xb, x, nx, CVXB_HOST, true, st));
+        if (beta != 0.0) CVXB_TRY(xfer_vec(yb, y, ny, CVXB_HOST, true, st));
+        xd = xb; yd = yb;
+    }
+    if (tr) CVXB_TRY(gemv_t(m, n, Gp, k->ldg, nullptr, xd, alpha, beta, yd, st));
+    else    CVXB_TRY(gemv_n(m, n, Gp, k->ldg, nullptr, xd, alpha, beta, yd, k->gemv_ws, st));
+    if (space != CVXB_DEVICE) CVXB_TRY(xfer_vec(y, yd, ny, CVXB_HOST, false, st));
+    CVXB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int cvxb_kkt_symv_H(cvxb_kkt *k, const double *x, double *y, double alpha, double beta, int space) {
+    if (!k || !x || !y) { set_error("symv_H: bad arguments"); return CVXB_E_ARG; }
+    if (!k->Hres) { set_error("symv_H: no resident H (call cvxb_kkt_set_H)"); return CVXB_E_ARG; }
+    CVXB_CUDA(cudaSetDevice(k->device));
+    const int n = k->n;
+    cudaStream_t st = k->st;
+    const double *xd = x; double *yd = y;
+    if (space != CVXB_DEVICE) {
+        CVXB_TRY(xfer_vec(k->xv, x, n, CVXB_HOST, true, st));
+        if (beta != 0.0) CVXB_TRY(xfer_vec(k->yv, y, n, CVXB_HOST, true, st));
+        xd = k->xv; yd = k->yv;
+    }
+    CVXB_TRY(gemv_t(n, n, k->Hres, kkt_ldk(k), nullptr, xd, alpha, beta, yd, st));
+    if (space != CVXB_DEVICE) CVXB_TRY(xfer_vec(y, yd, n, CVXB_HOST, false, st));
+    CVXB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

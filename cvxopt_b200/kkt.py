@@ -1,0 +1,253 @@
+"""`kktsolver` factories backed by the B200 library — host-side mirror of the
+reference's KKT factories (reference src/python/misc.py:1213-1349, `kkt_chol`).
+
+Usage with an unmodified CVXOPT (the plugin boundary, coneprog.py:323-344 /
+1658-1679):
+
+    from cvxopt import solvers
+    import cvxopt_b200
+    factor = cvxopt_b200.kkt_chol(G, dims, A, H=P)        # G, P uploaded once
+    sol = solvers.coneqp(P, q, G, h, dims, kktsolver=lambda W: factor(W))
+
+`factor(W, H=None, Df=None)` returns `solve(x, y, z)` which overwrites the
+solver-owned vectors in place with (ux, uy, W*uz), exactly like the reference
+closure.  Any object exposing the buffer protocol with fp64 column-major data
+works (cvxopt.matrix, numpy F-ordered arrays); cvxopt itself is not imported.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _mat(a, name="matrix"):
+    """fp64, column-major 2-D view (copy only if the layout requires it)."""
+    arr = np.asarray(a)
+    if arr.dtype != np.float64:
+        if arr.dtype.kind in "iuf":
+            arr = arr.astype(np.float64)
+        else:
+            raise TypeError("%s must be a real 'd' matrix" % name)
+    if arr.ndim == 1:
+        arr = arr.reshape(-1, 1)
+    if arr.ndim != 2:
+        raise TypeError("%s must be two-dimensional" % name)
+    if not arr.flags.f_contiguous:
+        arr = np.asfortranarray(arr)
+    return arr
+
+
+def _vec_inplace(a, n, name):
+    """writable fp64 view of a solver-owned vector of length n (no copy allowed)."""
+    arr = np.asarray(a)
+    if arr.dtype != np.float64 or arr.size != n:
+        raise TypeError("%s must be a 'd' matrix of size (%d,1)" % (name, n))
+    flat = arr.reshape(-1, order="F") if arr.ndim > 1 else arr
+    if not np.shares_memory(flat, arr) or not flat.flags.writeable or not flat.flags.c_contiguous:
+        raise TypeError("%s must be a contiguous writable buffer" % name)
+    return flat
+
+
+def make_dims(dims, mnl=0):
+    """reference `dims` dict -> (ctypes Dims, keep-alive tuple, cdim, cdim_pckd)"""
+    if dims is None:
+        raise TypeError("dims is required")
+    ml = int(dims["l"])
+    q = [int(k) for k in dims["q"]]
+    s = [int(k) for k in dims["s"]]
+    if ml < 0:
+        raise TypeError("'dims['l']' must be a nonnegative integer")
+    if any(k < 1 for k in q):
+        raise TypeError("'dims['q']' must be a list of positive integers")
+    if any(k < 0 for k in s):
+        raise TypeError("'dims['s']' must be a list of nonnegative integers")
+    qa = (C.c_int * max(1, len(q)))(*q)
+    sa = (C.c_int * max(1, len(s)))(*s)
+    d = _lib.Dims(int(mnl), ml, len(q), C.cast(qa, _lib.c_int_p), len(s), C.cast(sa, _lib.c_int_p))
+    cdim = mnl + ml + sum(q) + sum(k * k for k in s)
+    cdim_pckd = mnl + ml + sum(q) + sum(k * (k + 1) // 2 for k in s)
+    return d, (qa, sa), cdim, cdim_pckd
+
+
+def _flat(items, count, name):
+    """concatenate a list of matrices (W['v'], W['r'], ...) into one fp64 vector"""
+    if count == 0:
+        return np.zeros(0)
+    parts = [np.asarray(m, dtype=np.float64).reshape(-1, order="F") for m in items]
+    out = np.concatenate(parts) if parts else np.zeros(0)
+    if out.size != count:
+        raise ValueError("W['%s'] has %d entries, expected %d" % (name, out.size, count))
+    return np.ascontiguousarray(out)
+
+
+def make_scaling(W, ml, q, s, mnl=0):
+    """reference W dict -> (ctypes Scaling, keep-alive list)"""
+    keep = []
+
+    def ptr(a):
+        keep.append(a)
+        return a.ctypes.data if a.size else None
+
+    try:
+        d = _flat([W["d"]], ml, "d")
+        di = _flat([W["di"]], ml, "di")
+    except KeyError:
+        raise KeyError("missing item W['d'] or W['di']")       # misc_solvers.c:134
+    v = _flat(W["v"], sum(q), "v")
+    beta = np.ascontiguousarray(np.array([float(b) for b in W["beta"]], dtype=np.float64))
+    if beta.size != len(q):
+        raise ValueError("W['beta'] has %d entries, expected %d" % (beta.size, len(q)))
+    r = _flat(W["r"], sum(k * k for k in s), "r")
+    rti = _flat(W["rti"], sum(k * k for k in s), "rti")
+    if mnl:
+        dnl = _flat([W["dnl"]], mnl, "dnl")
+        dnli = _flat([W["dnli"]], mnl, "dnli")
+    else:
+        dnl = dnli = np.zeros(0)
+    sc = _lib.Scaling(ptr(dnl), ptr(dnli), ptr(d), ptr(di), ptr(v), ptr(beta), ptr(r), ptr(rti))
+    return sc, keep
+
+
+class KKTChol:
+    """One `kkt_chol` factory instance: G (and optionally H) resident in HBM."""
+
+    def __init__(self, G, dims, A=None, mnl=0, H=None, device=0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        Gm = _mat(G, "G")
+        self.n = Gm.shape[1]
+        self.dims = {"l": int(dims["l"]), "q": [int(k) for k in dims["q"]],
+                     "s": [int(k) for k in dims["s"]]}
+        self.mnl = int(mnl)
+        self._cd, self._keep, self.cdim, self.cdim_pckd = make_dims(self.dims, self.mnl)
+        if A is None:
+            p = 0
+            Am = None
+        else:
+            Am = _mat(A, "A")
+            p = Am.shape[0]
+            if p and Am.shape[1] != self.n:
+                raise TypeError("A must have %d columns" % self.n)
+        self.p = p
+        # the reference allocates Gs as (cdim, n) and copies G into rows mnl: (misc.py:1252,1270)
+        if Gm.shape[0] != self.cdim - self.mnl:
+            raise TypeError("G must be a 'd' matrix of size (%d, %d)" % (self.cdim - self.mnl, self.n))
+        if self.mnl:
+            full = np.zeros((self.cdim, self.n), order="F")
+            full[self.mnl:, :] = Gm
+            Gm = full
+        rc = self._lib.cvxb_kkt_create(
+            C.byref(self._h), self.n, p, C.byref(self._cd), Gm.ctypes.data, max(1, Gm.shape[0]),
+            Am.ctypes.data if (Am is not None and p) else None, max(1, p), _lib.HOST, device)
+        _lib.check(rc, "kkt_chol")
+        self._H_resident = None
+        if H is not None:
+            self.set_H(H)
+
+    # -- resident H ---------------------------------------------------------
+    def set_H(self, H):
+        Hm = _mat(H, "H")
+        if Hm.shape != (self.n, self.n):
+            raise TypeError("H must be a 'd' matrix of size (%d, %d)" % (self.n, self.n))
+        _lib.check(self._lib.cvxb_kkt_set_H(self._h, Hm.ctypes.data, max(1, self.n), _lib.HOST), "set_H")
+        self._H_resident = H
+
+    # -- factor(W, H, Df) -> solve ------------------------------------------
+    def factor(self, W, H=None, Df=None):
+        sc, keep = make_scaling(W, self.dims["l"], self.dims["q"], self.dims["s"], self.mnl)
+        # H is None            -> add the resident H if the factory was given one
+        # H is the resident H  -> no re-upload
+        # any other H          -> uploaded for this call (cvxprog passes a fresh H every time)
+        use_res = 0
+        Hp, ldh = None, 1
+        if H is None or H is self._H_resident:
+            use_res = 1 if self._H_resident is not None else 0
+        else:
+            Hm = _mat(H, "H")
+            if Hm.shape != (self.n, self.n):
+                raise TypeError("H must be a 'd' matrix of size (%d, %d)" % (self.n, self.n))
+            keep.append(Hm)
+            Hp, ldh = Hm.ctypes.data, max(1, self.n)
+        Dp, lddf = None, 1
+        if self.mnl:
+            if Df is None:
+                raise TypeError("Df is required when mnl > 0")
+            Dm = _mat(Df, "Df")
+            if Dm.shape != (self.mnl, self.n):
+                raise TypeError("Df must be a 'd' matrix of size (%d, %d)" % (self.mnl, self.n))
+            keep.append(Dm)
+            Dp, lddf = Dm.ctypes.data, max(1, self.mnl)
+        rc = self._lib.cvxb_kkt_factor(self._h, C.byref(sc), Hp, ldh, Dp, lddf, use_res, _lib.HOST)
+        _lib.check(rc, "factor")
+        return self.solve
+
+    def solve(self, x, y, z):
+        xv = _vec_inplace(x, self.n, "x")
+        zv = _vec_inplace(z, self.cdim, "z")
+        yp = None
+        if self.p:
+            yp = _vec_inplace(y, self.p, "y").ctypes.data
+        rc = self._lib.cvxb_kkt_solve(self._h, xv.ctypes.data, yp, zv.ctypes.data, _lib.HOST)
+        _lib.check(rc, "solve")
+
+    __call__ = factor
+
+    # -- device-resident operators for function-valued G / P -----------------
+    def G(self, x, y, alpha=1.0, beta=0.0, trans="N"):
+        """y := alpha*G*x + beta*y (trans 'N') or alpha*G'*x + beta*y ('T') on the resident G
+        (the function-valued G protocol, reference coneprog.py:1682-1711)."""
+        m = self.cdim - self.mnl
+        nx, ny = (m, self.n) if trans == "T" else (self.n, m)
+        xv = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, order="F"))
+        yv = _vec_inplace(y, ny, "y")
+        if xv.size != nx:
+            raise TypeError("x must have %d entries" % nx)
+        rc = self._lib.cvxb_kkt_gemv_G(self._h, xv.ctypes.data, yv.ctypes.data, float(alpha),
+                                       float(beta), ord(trans), _lib.HOST)
+        _lib.check(rc, "G operator")
+
+    def P(self, x, y, alpha=1.0, beta=0.0):
+        """y := alpha*H*x + beta*y on the resident H (function-valued P protocol)."""
+        xv = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, order="F"))
+        yv = _vec_inplace(y, self.n, "y")
+        rc = self._lib.cvxb_kkt_symv_H(self._h, xv.ctypes.data, yv.ctypes.data, float(alpha),
+                                       float(beta), _lib.HOST)
+        _lib.check(rc, "P operator")
+
+    # -- introspection ---------------------------------------------------------
+    def last_ms(self):
+        f, s = C.c_double(), C.c_double()
+        self._lib.cvxb_kkt_last_ms(self._h, C.byref(f), C.byref(s))
+        return f.value, s.value
+
+    def last_breakdown(self):
+        b = (C.c_double * 3)()
+        self._lib.cvxb_kkt_last_breakdown(self._h, b)
+        return {"syrk_ms": b[0], "potrf_ms": b[1], "scale_ms": b[2]}
+
+    def get_L(self):
+        L = np.zeros((self.n, self.n), order="F")
+        _lib.check(self._lib.cvxb_kkt_get_L(self._h, L.ctypes.data, max(1, self.n)), "get_L")
+        return np.tril(L)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.cvxb_kkt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def kkt_chol(G, dims, A=None, mnl=0, H=None, device=0):
+    """Drop-in for `misc.kkt_chol(G, dims, A, mnl)` (reference misc.py:1213).
+
+    Returns `factor(W, H=None, Df=None)`; `factor` returns `solve(x, y, z)`.
+    Extra keyword `H`: a constant Hessian block (coneqp's P) made resident once,
+    so `factor(W)` / `factor(W, P)` do not re-upload n^2 doubles per iteration.
+    """
+    return KKTChol(G, dims, A, mnl, H, device)

@@ -1,0 +1,164 @@
+/*
+ * cvxopt_b200 — C ABI of the B200-native KKT hot path of CVXOPT's cone solvers.
+ *
+ * Every entry point below is what a CVXOPT-side binding for this path would
+ * bind (ctypes / CPython C-API).  Plain pointers and sizes
+ * only; no torch / Python types.  All matrices are fp64, column-major (the
+ * layout of cvxopt's `matrix`, reference src/C/cvxopt.h:48-56), all index
+ * arguments are 0-based element counts.
+ *
+ * Cone layout of every "cone vector" (reference src/python/coneprog.py:79-96):
+ *   [ mnl nonlinear | ml 'l' | q[0] .. q[nq-1] 'q' blocks | s[0]^2 .. 's' blocks ]
+ *   cdim      = mnl + ml + sum q + sum s^2        (unpacked, 's' blocks full col-major)
+ *   cdim_pckd = mnl + ml + sum q + sum s(s+1)/2   (packed lower, off-diag * sqrt 2)
+ *
+ * Return codes (all int-returning functions):
+ *    0   success
+ *   >0   LAPACK-style `info`: leading minor of that order is not positive
+ *        definite (the reference raises ArithmeticError for this,
+ *        src/C/lapack.c:32-34) — Python layer raises ArithmeticError
+ *   <0   CVXB_E_* below (bad argument / CUDA failure); cvxb_last_error() has text
+ */
+#ifndef CVXOPT_B200_H
+#define CVXOPT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVXB_E_ARG     (-1)   /* invalid argument (ValueError in the reference, misc.h:78-110) */
+#define CVXB_E_CUDA    (-2)   /* CUDA runtime error */
+#define CVXB_E_NOMEM   (-3)   /* allocation failure */
+#define CVXB_E_NOGPU   (-4)   /* no usable sm_100 device: the product path has NO CPU fallback */
+#define CVXB_E_UNSUP   (-5)   /* valid in the reference but not built yet (e.g. p > 0) */
+
+/* memory space of the pointers handed to a call */
+#define CVXB_HOST   0
+#define CVXB_DEVICE 1
+
+typedef struct cvxb_kkt cvxb_kkt;     /* opaque: one kkt_chol factory instance  */
+typedef struct cvxb_batch cvxb_batch; /* opaque: batch of independent dense QPs */
+
+/* cone dimensions: mirror of the reference `dims` dict + mnl */
+typedef struct {
+    int mnl;          /* nonlinear rows (cvxprog), 0 for conelp/coneqp            */
+    int ml;           /* dims['l']                                                 */
+    int nq;           /* len(dims['q'])                                            */
+    const int *q;     /* dims['q'][k]                                              */
+    int ns;           /* len(dims['s'])                                            */
+    const int *s;     /* dims['s'][k]                                              */
+} cvxb_dims;
+
+/* Nesterov-Todd scaling: flat mirror of the reference `W` dict
+ * (src/python/coneprog.py:327-334, src/python/misc.py:45-56) */
+typedef struct {
+    const double *dnl, *dnli;   /* mnl each (may be NULL when mnl == 0)           */
+    const double *d, *di;       /* ml each                                         */
+    const double *v;            /* W['v'][0] | W['v'][1] | ...   (sum q)           */
+    const double *beta;         /* nq                                              */
+    const double *r, *rti;      /* W['r'][k] / W['rti'][k], s[k] x s[k] col-major,
+                                   concatenated (sum s^2)                          */
+} cvxb_scaling;
+
+/* ---- library / device ---------------------------------------------------- */
+const char *cvxb_last_error(void);
+int  cvxb_device_count(void);                 /* sm_100 devices visible            */
+int  cvxb_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+unsigned long long cvxb_launch_count(void);
+/* cudaMalloc/cudaFree/cudaMemcpy shims so a ctypes-only host needs no CUDA binding */
+int  cvxb_malloc(void **dptr, unsigned long long bytes);
+int  cvxb_free(void *dptr);
+int  cvxb_memcpy_h2d(void *dst, const void *src, unsigned long long bytes);
+int  cvxb_memcpy_d2h(void *dst, const void *src, unsigned long long bytes);
+int  cvxb_sync(void);
+
+/* ---- kkt_chol factory:  replaces misc.kkt_chol(G, dims, A, mnl)
+ *      reference src/python/misc.py:1213-1255.
+ * G is cdim x n (rows mnl.. hold G; the mnl leading rows are Df, given per
+ * factor call).  G is uploaded ONCE and stays resident in HBM.
+ * space = CVXB_HOST: G/A are host pointers (copied); CVXB_DEVICE: device
+ * pointers that are ADOPTED without copy (caller keeps them alive). */
+int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims,
+                    const double *G, int ldg, const double *A, int lda,
+                    int space, int device);
+void cvxb_kkt_destroy(cvxb_kkt *k);
+
+/* Make H (n x n, lower triangle significant) resident; later factor calls with
+ * H == NULL and use_resident_H=1 add it.  coneqp passes the same P every
+ * iteration (coneprog.py:1980-1981) — this avoids re-uploading n^2 doubles. */
+int cvxb_kkt_set_H(cvxb_kkt *k, const double *H, int ldh, int space);
+
+/* factor: replaces the closure `factor(W, H, Df)`  misc.py:1257-1282
+ *   Gs = pack(W^{-T} [Df; G]);  K = Gs'Gs + H (lower);  K = L L'
+ * W pointers live in `space`.  H/Df may be NULL.  use_resident_H: add the
+ * matrix given to cvxb_kkt_set_H.  Returns info>0 on a non-positive pivot. */
+int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *W, const double *H, int ldh,
+                    const double *Df, int lddf, int use_resident_H, int space);
+
+/* solve: replaces the closure `solve(x, y, z)`  misc.py:1284-1345.
+ * In place: (bx, by, bz) -> (ux, uy, W*uz).  x: n, y: p, z: cdim. */
+int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space);
+
+/* read back pieces for tests: the Cholesky factor (n x n lower) */
+int cvxb_kkt_get_L(cvxb_kkt *k, double *L_host, int ldl);
+/* timing of the last factor/solve in ms (CUDA events on the library stream) */
+int cvxb_kkt_last_ms(cvxb_kkt *k, double *factor_ms, double *solve_ms);
+/* per-kernel-class CUDA-event breakdown of the last factor (syrk, potrf, scale) */
+int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3);
+
+/* device-resident G / P operators for the function-valued G(x,y,alpha,beta,trans)
+ * / P(x,y,alpha,beta) protocol of coneprog (coneprog.py:1682-1711):
+ *   y := alpha*G*x + beta*y  (trans 'N')   or   y := alpha*G'*x + beta*y ('T')
+ *   y := alpha*H*x + beta*y  (H symmetric, lower stored) */
+int cvxb_kkt_gemv_G(cvxb_kkt *k, const double *x, double *y, double alpha, double beta,
+                    int trans, int space);
+int cvxb_kkt_symv_H(cvxb_kkt *k, const double *x, double *y, double alpha, double beta,
+                    int space);
+
+/* ---- cone algebra: mirror of src/C/misc_solvers.c (12 entry points,
+ * misc_solvers.c:1155-1173).  x is xr x xc column-major with leading
+ * dimension xr; everything in place as in the reference. */
+int cvxb_scale(double *x, int xr, int xc, const cvxb_dims *dims, const cvxb_scaling *W,
+               int trans /*'N'|'T'*/, int inverse /*'N'|'I'*/, int space); /* misc_solvers.c:85  */
+int cvxb_scale2(const double *lmbda, double *x, const cvxb_dims *dims, int inverse,
+                int space);                                                  /* :256 */
+int cvxb_pack(const double *x, double *y, const cvxb_dims *dims, int space); /* :412 */
+int cvxb_pack2(double *x, int xr, int xc, const cvxb_dims *dims, int space); /* :476 */
+int cvxb_unpack(const double *x, double *y, const cvxb_dims *dims, int space); /* :552 */
+int cvxb_symm(double *x, int n, int space);                                  /* :610 */
+int cvxb_sprod(double *x, const double *y, const cvxb_dims *dims, int diag, int space);  /* :634 */
+int cvxb_sinv(double *x, const double *y, const cvxb_dims *dims, int space); /* :775 */
+int cvxb_trisc(double *x, const cvxb_dims *dims, int space);                 /* :887 */
+int cvxb_triusc(double *x, const cvxb_dims *dims, int space);                /* :940 */
+int cvxb_sdot(const double *x, const double *y, const cvxb_dims *dims, double *result,
+              int space);                                                    /* :991 */
+int cvxb_max_step(double *x, const cvxb_dims *dims, double *sigma, double *result,
+                  int space);                                                /* :1052 */
+
+/* ---- dense building blocks (the BLAS/LAPACK calls of the path, device pointers):
+ * blas.syrk(trans='T') blas.c:3039 fused with the 'l' row scaling;
+ * lapack.potrf lapack.c:1471; lapack.potrs lapack.c:1553. */
+int cvxb_syrk_scaled(int n, int k, const double *A, int lda, const double *rowscale,
+                     const double *H, int ldh, double *C, int ldc, int device);
+int cvxb_potrf(int n, double *A, int lda, double *work_inv /* n x 128 */, int device);
+int cvxb_potrs(int n, const double *L, int ldl, const double *inv, double *b, int device);
+/* plain C = alpha * op(A) op(B) + beta*C on the DMMA kernel (tests / 's' congruence) */
+int cvxb_gemm(int transa, int transb, int m, int n, int k, double alpha, const double *A,
+              int lda, const double *B, int ldb, double beta, double *C, int ldc, int device);
+
+/* ---- batch of independent dense QPs (BASELINE config 4): one problem per
+ * CTA-group, lock-step primal-dual IPM fully on device (oracle: a Python loop
+ * over solvers.qp).  Problems are  min 1/2 x'P x + q'x  s.t.  G x <= h. */
+int cvxb_batch_create(cvxb_batch **out, int nprob, int n, int m, int device);
+void cvxb_batch_destroy(cvxb_batch *b);
+int cvxb_batch_load(cvxb_batch *b, const double *P, const double *q, const double *G,
+                    const double *h, int space);
+int cvxb_batch_solve(cvxb_batch *b, int maxiters, double abstol, double reltol, double feastol);
+int cvxb_batch_results(cvxb_batch *b, double *x, double *s, double *z, int *status,
+                       int *iters, double *pobj, double *dobj, int space);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVXOPT_B200_H */

@@ -1,0 +1,260 @@
+"""TEST INFRASTRUCTURE — CPU restatement (numpy/scipy) of the reference's KKT hot path.
+
+This module is the *oracle*: a plain restatement of what CVXOPT computes on the
+path  NT scaling -> normal equations -> Cholesky -> solves.  It is imported only
+by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline arm; nothing under
+cvxopt_b200/ may import it.  Parity pinning: tests/test_oracle_vs_reference.py
+checks every function here against the reference itself (oracle/_ref, built from
+/root/reference by oracle/build_ref.sh) and against the committed golden vectors
+in tests/golden/ (generated from the reference by tests/golden/make_golden.py).
+
+All citations are relative to /root/reference.  Vectors/matrices are numpy fp64,
+column-major; a "cone vector" is laid out [mnl | l | q blocks | s blocks (n^2 each)].
+"""
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+
+def cone_sizes(dims, mnl=0):
+    ml, q, s = int(dims["l"]), list(dims["q"]), list(dims["s"])
+    cdim = mnl + ml + sum(q) + sum(k * k for k in s)
+    cdim_pckd = mnl + ml + sum(q) + sum(k * (k + 1) // 2 for k in s)
+    return ml, q, s, cdim, cdim_pckd
+
+
+# --------------------------------------------------------------------------- scale
+def scale(x, W, trans="N", inverse="N"):
+    """In place x := W x, W' x, W^{-1} x, W^{-T} x.  src/C/misc_solvers.c:85-244
+    (python twin src/python/misc.py:30-164).  x: (rows, cols) F-ordered ndarray."""
+    if x.ndim == 1:
+        x = x.reshape(-1, 1)
+    ind = 0
+    if "dnl" in W:                                      # misc_solvers.c:117-124
+        w = np.asarray(W["dnl"] if inverse == "N" else W["dnli"]).reshape(-1)
+        x[ind:ind + w.size, :] *= w[:, None]
+        ind += w.size
+    w = np.asarray(W["d"] if inverse == "N" else W["di"]).reshape(-1)   # :132-141
+    x[ind:ind + w.size, :] *= w[:, None]
+    ind += w.size
+    for k, vk in enumerate(W["v"]):                     # :158-183
+        v = np.asarray(vk).reshape(-1)
+        m = v.size
+        blk = x[ind:ind + m, :]
+        if inverse == "I":
+            blk[0, :] *= -1.0
+        w = v @ blk
+        blk[0, :] *= -1.0
+        blk += 2.0 * np.outer(v, w)
+        if inverse == "I":
+            blk[0, :] *= -1.0
+            a = 1.0 / float(W["beta"][k])
+        else:
+            a = float(W["beta"][k])
+        blk *= a
+        ind += m
+    rs = W["r"] if inverse == "N" else W["rti"]         # :203-240
+    for rk in rs:
+        r = np.asarray(rk)
+        n = r.shape[0]
+        right = (inverse == "N" and trans == "T") or (inverse == "I" and trans == "N")
+        for i in range(x.shape[1]):
+            X = x[ind:ind + n * n, i].reshape(n, n, order="F")
+            Lx = np.tril(X).copy()
+            Lx[np.diag_indices(n)] *= 0.5               # :219
+            if right:                                   # wrk = r * tril(x);  x = r wrk' + wrk r'
+                wrk = r @ Lx
+                Y = r @ wrk.T + wrk @ r.T
+            else:                                       # wrk = tril(x) * r;  x = r' wrk + wrk' r
+                wrk = Lx @ r
+                Y = r.T @ wrk + wrk.T @ r
+            il = np.tril_indices(n)
+            X[il] = Y[il]                               # dsyr2k 'L': upper triangle untouched
+            x[ind:ind + n * n, i] = X.reshape(-1, order="F")
+        ind += n * n
+    return x
+
+
+# --------------------------------------------------------------------------- pack / unpack
+def pack(x, y, dims, mnl=0, offsetx=0, offsety=0):
+    """misc_solvers.c:412-465 (vector version; diagonal goes through /sqrt2 then *sqrt2)."""
+    ml, q, s, _, _ = cone_sizes(dims, mnl)
+    nlq = mnl + ml + sum(q)
+    y[offsety:offsety + nlq] = x[offsetx:offsetx + nlq]
+    iu, ip = offsetx + nlq, offsety + nlq
+    ip0 = ip
+    for n in s:
+        for k in range(n):
+            ln = n - k
+            y[ip:ip + ln] = x[iu + k * (n + 1): iu + k * (n + 1) + ln]
+            y[ip] /= math.sqrt(2.0)
+            ip += ln
+        iu += n * n
+    y[ip0:ip] *= math.sqrt(2.0)
+    return y
+
+
+def pack2(x, dims, mnl=0):
+    """misc_solvers.c:476-541: in place on the columns of x (rows compacted)."""
+    ml, q, s, _, _ = cone_sizes(dims, mnl)
+    nlq = mnl + ml + sum(q)
+    iu = ip = nlq
+    a = math.sqrt(2.0)
+    for n in s:
+        for k in range(n):
+            ln = n - k
+            wrk = x[iu + k * (n + 1): iu + k * (n + 1) + ln, :].copy()
+            wrk[1:, :] *= a
+            x[ip:ip + ln, :] = wrk
+            ip += ln
+        iu += n * n
+    return x
+
+
+def unpack(x, y, dims, mnl=0, offsetx=0, offsety=0):
+    """misc_solvers.c:552-601."""
+    ml, q, s, _, _ = cone_sizes(dims, mnl)
+    m = mnl + ml + sum(q)
+    y[offsety:offsety + m] = x[offsetx:offsetx + m]
+    ip, iu = offsetx + m, offsety + m
+    a = 1.0 / math.sqrt(2.0)
+    for n in s:
+        for k in range(n):
+            ln = n - k
+            y[iu + k * (n + 1): iu + k * (n + 1) + ln] = x[ip:ip + ln]
+            ip += ln
+            y[iu + k * (n + 1) + 1: iu + k * (n + 1) + ln] *= a
+        iu += n * n
+    return y
+
+
+def symm(x, n, offset=0):
+    """misc_solvers.c:610-625: fill the upper triangle from the lower one."""
+    X = x[offset:offset + n * n].reshape(n, n, order="F")
+    il = np.tril_indices(n, -1)
+    X.T[il] = X[il]
+    return x
+
+
+# --------------------------------------------------------------------------- hyperbolic helpers
+def jnrm2(x, n=None, offset=0):
+    """sqrt(x' J x), J = diag(1,-I).  src/python/misc.py:848-856"""
+    if n is None:
+        n = len(x)
+    a = np.linalg.norm(x[offset + 1: offset + n])
+    return math.sqrt(x[offset] - a) * math.sqrt(x[offset] + a)
+
+
+def jdot(x, y, n=None, offsetx=0, offsety=0):
+    """x' J y.  misc.py:835-845"""
+    if n is None:
+        n = len(x)
+    return x[offsetx] * y[offsety] - float(
+        np.dot(x[offsetx + 1: offsetx + n], y[offsety + 1: offsety + n]))
+
+
+# --------------------------------------------------------------------------- NT scaling
+def compute_scaling(s, z, lmbda, dims, mnl=None):
+    """misc.py:250-419.  Returns the dict W; writes lmbda."""
+    W = {}
+    if mnl is None:
+        mnl = 0
+    else:
+        W["dnl"] = np.sqrt(s[:mnl] / z[:mnl])
+        W["dnli"] = W["dnl"] ** -1
+        lmbda[:mnl] = np.sqrt(s[:mnl] * z[:mnl])
+    m = dims["l"]
+    W["d"] = np.sqrt(s[mnl:mnl + m] / z[mnl:mnl + m])
+    W["di"] = W["d"] ** -1
+    lmbda[mnl:mnl + m] = np.sqrt(s[mnl:mnl + m] * z[mnl:mnl + m])
+    ind = mnl + dims["l"]
+    W["v"] = [np.zeros(k) for k in dims["q"]]
+    W["beta"] = len(dims["q"]) * [0.0]
+    for k in range(len(dims["q"])):
+        m = dims["q"][k]
+        v = W["v"][k]
+        aa = jnrm2(s, offset=ind, n=m)
+        bb = jnrm2(z, offset=ind, n=m)
+        W["beta"][k] = math.sqrt(aa / bb)
+        cc = math.sqrt((float(np.dot(s[ind:ind + m], z[ind:ind + m])) / aa / bb + 1.0) / 2.0)
+        v[:] = z[ind:ind + m]
+        v *= -1.0 / bb
+        v[0] *= -1.0
+        v += (1.0 / aa) * s[ind:ind + m]
+        v *= 1.0 / 2.0 / cc
+        v[0] += 1.0
+        v *= 1.0 / math.sqrt(2.0 * v[0])
+        lmbda[ind] = cc
+        dd = 2 * cc + s[ind] / aa + z[ind] / bb
+        lmbda[ind + 1: ind + m] = s[ind + 1: ind + m]
+        lmbda[ind + 1: ind + m] *= (cc + z[ind] / bb) / dd / aa
+        lmbda[ind + 1: ind + m] += ((cc + s[ind] / aa) / dd / bb) * z[ind + 1: ind + m]
+        lmbda[ind: ind + m] *= math.sqrt(aa * bb)
+        ind += m
+    W["r"] = [np.zeros((m, m), order="F") for m in dims["s"]]
+    W["rti"] = [np.zeros((m, m), order="F") for m in dims["s"]]
+    ind2 = ind
+    for k in range(len(dims["s"])):
+        m = dims["s"][k]
+        Ls = np.linalg.cholesky(_symL(s[ind2:ind2 + m * m], m))      # :386-391
+        Lz = np.linalg.cholesky(_symL(z[ind2:ind2 + m * m], m))
+        U, sv, _ = np.linalg.svd(Lz.T @ Ls)                          # :397-399
+        lmbda[ind:ind + m] = sv
+        r = sla.solve_triangular(Lz, U, lower=True, trans="T")       # :402-403
+        rti = Lz @ U                                                 # :406-407
+        a = np.sqrt(sv)
+        W["r"][k][:, :] = r * a[None, :]
+        W["rti"][k][:, :] = rti / a[None, :]
+        ind += m
+        ind2 += m * m
+    return W
+
+
+def _symL(x, m):
+    X = np.array(x, dtype=float).reshape(m, m, order="F")
+    return np.tril(X) + np.tril(X, -1).T
+
+
+# --------------------------------------------------------------------------- kkt_chol
+class KktChol:
+    """misc.kkt_chol for p == 0 (misc.py:1213-1349): factor(W, H, Df) -> solve(x, y, z)."""
+
+    def __init__(self, G, dims, A=None, mnl=0):
+        self.G = np.asfortranarray(np.asarray(G, dtype=float))
+        self.dims = dims
+        self.mnl = mnl
+        self.n = self.G.shape[1]
+        _, _, _, self.cdim, self.cdim_pckd = cone_sizes(dims, mnl)
+        if A is not None and np.asarray(A).shape[0] > 0:
+            raise NotImplementedError("oracle restatement covers p == 0")
+
+    def factor(self, W, H=None, Df=None):
+        n, mnl = self.n, self.mnl
+        Gs = np.zeros((self.cdim, n), order="F")                     # :1252
+        if mnl:
+            Gs[:mnl, :] = Df
+        Gs[mnl:, :] = self.G                                         # :1270
+        scale(Gs, W, trans="T", inverse="I")                         # :1271
+        pack2(Gs, self.dims, mnl)                                    # :1272
+        Gp = Gs[:self.cdim_pckd, :]
+        K = Gp.T @ Gp                                                # blas.syrk trans='T'  :1275
+        if H is not None:
+            K = K + np.tril(np.asarray(H)) + np.tril(np.asarray(H), -1).T   # :1276-1277
+        try:
+            L = np.linalg.cholesky(K)                                # lapack.potrf  :1282
+        except np.linalg.LinAlgError:
+            raise ArithmeticError("potrf: not positive definite")
+        self.Gs, self.L, self.W = Gp, L, W
+        return self.solve
+
+    def solve(self, x, y, z):
+        """In place (bx, by, bz) -> (ux, uy, W uz).  misc.py:1284-1345"""
+        zc = z.reshape(-1, 1)
+        scale(zc, self.W, trans="T", inverse="I")                    # :1306
+        bzp = np.zeros(self.cdim_pckd)
+        pack(z, bzp, self.dims, self.mnl)                            # :1307
+        x += self.Gs.T @ bzp                                         # :1311
+        x[:] = sla.cho_solve((self.L, True), x)                      # :1327
+        bzp = self.Gs @ x - bzp                                      # :1344
+        unpack(bzp, z, self.dims, self.mnl)                          # :1345

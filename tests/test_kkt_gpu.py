@@ -1,0 +1,147 @@
+"""GPU parity tests of the KKT path through the C-ABI: cvxopt_b200.kkt_chol vs the
+numpy oracle (oracle/kkt_oracle.py), which is itself pinned to the reference by
+tests/test_oracle_vs_reference.py.  Tolerance: north_star's 1e-10 on the search
+direction (relative, 2-norm)."""
+import numpy as np
+import pytest
+
+import kkt_oracle as ko
+from problems import cone_dim, dense_qp, random_scaling
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def packed(z, dims):
+    _, _, _, _, cp = ko.cone_sizes(dims)
+    out = np.zeros(cp)
+    ko.pack(z.copy(), out, dims)
+    return out
+
+
+def run_case(dims, n, seed, with_H=True, resident=False):
+    import cvxopt_b200
+    rng = np.random.Generator(np.random.PCG64(seed))
+    K = cone_dim(dims)
+    G = np.asfortranarray(rng.standard_normal((K, n)))
+    H = None
+    if with_H:
+        B = rng.standard_normal((n, n))
+        H = np.asfortranarray(B @ B.T / n + np.eye(n))
+    W, _ = random_scaling(dims, seed=seed + 1)
+    fac = cvxopt_b200.kkt_chol(G, dims, None, H=H if resident else None)
+    solve = fac(W) if (resident or H is None) else fac(W, H)
+    f_or = ko.KktChol(G, dims).factor(W, H)
+    for rep in range(2):
+        x, z = rng.standard_normal(n), rng.standard_normal(K)
+        xo, zo = x.copy(), z.copy()
+        solve(x, None, z)
+        f_or(xo, None, zo)
+        assert relerr(x, xo) < TOL, ("x", relerr(x, xo))
+        assert relerr(packed(z, dims), packed(zo, dims)) < TOL, ("z", relerr(packed(z, dims), packed(zo, dims)))
+    L = fac.get_L()
+    assert relerr(L, f_or.__self__.L) < 1e-9
+    fac.close()
+
+
+@pytest.mark.parametrize("n,m,seed", [(1, 1, 0), (3, 7, 1), (64, 100, 2), (200, 400, 3), (257, 391, 4), (513, 1100, 5)])
+def test_l_cones(n, m, seed):
+    run_case({"l": m, "q": [], "s": []}, n, seed)
+
+
+def test_l_cones_no_H():
+    run_case({"l": 300, "q": [], "s": []}, 150, 7, with_H=False)
+
+
+def test_l_cones_resident_H():
+    run_case({"l": 300, "q": [], "s": []}, 150, 8, resident=True)
+
+
+@pytest.mark.parametrize("q,n,seed", [([5], 4, 0), ([64] * 8, 128, 1), ([3, 1, 70, 33], 50, 2)])
+def test_q_cones(q, n, seed):
+    run_case({"l": 0, "q": q, "s": []}, n, seed)
+
+
+@pytest.mark.parametrize("s,n,seed", [([3], 4, 0), ([1, 10, 33], 40, 1), ([64], 48, 2), ([130], 20, 3)])
+def test_s_cones(s, n, seed):
+    run_case({"l": 0, "q": [], "s": s}, n, seed)
+
+
+def test_mixed_cones():
+    run_case({"l": 37, "q": [9, 64, 2], "s": [5, 17]}, 90, 11)
+    run_case({"l": 5, "q": [4], "s": [3]}, 3, 12, with_H=False)
+
+
+def test_indefinite_raises_arithmetic_error():
+    import cvxopt_b200
+    n = 40
+    dims = {"l": 10, "q": [], "s": []}
+    rng = np.random.Generator(np.random.PCG64(0))
+    G = np.asfortranarray(rng.standard_normal((10, n)))     # rank 10 < n and no H: singular
+    W, _ = random_scaling(dims, 1)
+    fac = cvxopt_b200.kkt_chol(G, dims)
+    with pytest.raises(ArithmeticError):
+        fac(W)
+    H = -np.eye(n)
+    with pytest.raises(ArithmeticError):
+        fac(W, np.asfortranarray(H))
+
+
+def test_ill_conditioned_scaling():
+    """late-IPM regime: d spans 1e8"""
+    import cvxopt_b200
+    n, m = 120, 300
+    P, q, G, h = dense_qp(n, m, seed=5)
+    rng = np.random.Generator(np.random.PCG64(1))
+    d = 10.0 ** rng.uniform(-4, 4, m)
+    W = {"d": d, "di": 1.0 / d, "v": [], "beta": [], "r": [], "rti": []}
+    dims = {"l": m, "q": [], "s": []}
+    fac = cvxopt_b200.kkt_chol(G, dims, H=P)
+    solve = fac(W)
+    f_or = ko.KktChol(G, dims).factor(W, P)
+    x, z = rng.standard_normal(n), rng.standard_normal(m)
+    xo, zo = x.copy(), z.copy()
+    solve(x, None, z)
+    f_or(xo, None, zo)
+    # both are backward-stable solves of a system with cond ~1e16*...; compare through the
+    # KKT residual of each instead of against each other when conditioning is extreme
+    assert relerr(x, xo) < 1e-6
+    assert relerr(z, zo) < 1e-6
+
+
+def test_building_blocks_gemm_potrf():
+    """cvxb_gemm / cvxb_potrf / cvxb_potrs on device pointers vs numpy (torch only moves memory)."""
+    import ctypes as C
+    import torch
+    from cvxopt_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.Generator(np.random.PCG64(4))
+    for (m, n, k, ta, tb) in [(130, 70, 45, "N", "N"), (257, 129, 300, "T", "N"), (64, 200, 33, "N", "T"), (100, 100, 100, "T", "T")]:
+        A = rng.standard_normal((k, m) if ta == "T" else (m, k))
+        B = rng.standard_normal((n, k) if tb == "T" else (k, n))
+        Cm = rng.standard_normal((m, n))
+        dA = torch.from_numpy(np.ascontiguousarray(A.T)).cuda()      # column-major buffers
+        dB = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()
+        dC = torch.from_numpy(np.ascontiguousarray(Cm.T)).cuda()
+        rc = lib.cvxb_gemm(ord(ta), ord(tb), m, n, k, 0.7, dA.data_ptr(), A.shape[0], dB.data_ptr(), B.shape[0], -0.3, dC.data_ptr(), m, 0)
+        assert rc == 0, _lib.last_error()
+        ref = 0.7 * (A.T if ta == "T" else A) @ (B.T if tb == "T" else B) - 0.3 * Cm
+        assert relerr(dC.cpu().numpy().T, ref) < 1e-13
+    for n in (1, 100, 128, 129, 700):
+        B = rng.standard_normal((n, n))
+        S = B @ B.T + n * np.eye(n)
+        dS = torch.from_numpy(S.copy()).cuda()                         # symmetric: layout-agnostic
+        inv = torch.zeros(((n + 127) // 128 + 1) * 128 * 128, dtype=torch.float64, device="cuda")
+        rc = lib.cvxb_potrf(n, dS.data_ptr(), n, inv.data_ptr(), 0)
+        assert rc == 0, _lib.last_error()
+        L = np.tril(dS.cpu().numpy().T)
+        assert relerr(L, np.linalg.cholesky(S)) < 1e-12
+        b = rng.standard_normal(n)
+        db = torch.from_numpy(b.copy()).cuda()
+        rc = lib.cvxb_potrs(n, dS.data_ptr(), n, inv.data_ptr(), db.data_ptr(), 0)
+        assert rc == 0
+        assert relerr(db.cpu().numpy(), np.linalg.solve(S, b)) < 1e-11
