@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — KKT factor+solve throughput of the cone-program hot path on B200.
+
+A "step" is one interior-point iteration's KKT work on the north-star workload
+(dense QP n=8192, m=2n 'l' cone rows): 1 factor (NT scaling fused into the
+normal-equations SYRK + Cholesky) and 2 solves (affine + combined direction;
+coneqp with refinement 0, reference src/python/coneprog.py:2256, 2360-2401).
+
+  value  : algorithmic GF/s (F_it / step time) with every input resident
+           in HBM, timed with CUDA events on the library's launch stream.
+  e2e    : the same metric through the public plugin call a CVXOPT user makes
+           (cvxopt_b200.kkt_chol -> factor(W) -> solve(x,y,z)) with pinned HOST buffers;
+           H2D/D2H copies inside the timed region.
+  --impl reference : the unmodified reference path (oracle/_ref: cvxopt's misc.kkt_chol +
+           OpenBLAS) on the box's host cores, same workload and metric.
+
+N > 1 GPUs: a single factorisation does not shard -> N independent
+replicas, one per rank, weak scaling; value = total flops / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kkt_factor_solve_gflops_fp64"
+FP64_DMMA_PEAK_TFLOPS = 37.2   # tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peaks.md)
+
+
+def flops(n, m, refinement=0):
+    f_fac = float(n) * n * m + float(n) ** 3 / 3.0          # SYRK n^2 Kp + POTRF n^3/3
+    f_sol = 4.0 * m * n + 2.0 * float(n) * n
+    return f_fac, f_sol, f_fac + 2 * (1 + refinement) * f_sol
+
+
+def make_problem(n, m, seed):
+    """SURVEY.md §8(d) dense QP generator (numpy PCG64)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    A0 = rng.standard_normal((n, n))
+    P = np.asfortranarray(A0.T @ A0 / n + np.eye(n))
+    del A0
+    G = np.asfortranarray(rng.standard_normal((n, m)).T)     # m x n, column-major
+    # mid-IPM scaling: d spans ~4 decades
+    d = 10.0 ** rng.uniform(-2.0, 2.0, m)
+    return P, G, d, rng
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4)
+                          if len(s) >= 7 and s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference's own kkt_chol (oracle/_ref) on host cores, same step."""
+    if rank != 0:
+        return
+    n, m = args.n, args.m
+    f_fac, f_sol, f_it = flops(n, m)
+    base = {"metric": METRIC, "unit": "GF/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "dense QP KKT step n=%d m=%d: 1 factor + 2 solves (kkt_chol)" % (n, m)}}
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "cvxopt")):
+        base["unavailable"] = "oracle/_ref not built (oracle/build_ref.sh needs /root/reference)"
+        print(json.dumps(base))
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(cores, 64)))
+    sys.path.insert(0, ref_dir)
+    from cvxopt import matrix, misc
+    P, G, d, rng = make_problem(n, m, args.seed)
+    Gm, Pm = matrix(G), matrix(P)
+    dims = {"l": m, "q": [], "s": []}
+    factor = misc.kkt_chol(Gm, dims, matrix(0.0, (0, n)))
+    W = {"d": matrix(d), "di": matrix(1.0 / d), "v": [], "beta": [], "r": [], "rti": []}
+    y = matrix(0.0, (0, 1))
+
+    def step():
+        f = factor(W, Pm)
+        for _ in range(2):
+            x, z = matrix(rng.standard_normal(n)), matrix(rng.standard_normal(m))
+            f(x, y, z)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    val = f_it / (ms * 1e-3) * 1e-9
+    base.update({"value": val, "ms_per_step": ms,
+                 "cpu_baseline": {"value": val, "unit": "GF/s", "cores": min(cores, 64), "kind": "reference",
+                                  "sample": "%d full-size steps after %d warm-up (misc.kkt_chol, scipy-openblas)"
+                                            % (args.steps, args.warmup)},
+                 "e2e": {"value": val, "unit": "GF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(base))
+
+
+def cpu_baseline_sample(args, P, G, d):
+    """Bounded sample of the reference path on this box's host cores (rank 0, N=1)."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "cvxopt")):
+        return {"value": None, "unit": "GF/s", "cores": 0, "kind": "reference",
+                "sample": "oracle/_ref not built"}
+    code = r"""
+import os, sys, json, time
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bench
+from cvxopt import matrix, misc
+n, m, seed = %d, %d, %d
+P, G, d, rng = bench.make_problem(n, m, seed)
+factor = misc.kkt_chol(matrix(G), {'l': m, 'q': [], 's': []}, matrix(0.0, (0, n)))
+W = {'d': matrix(d), 'di': matrix(1.0 / d), 'v': [], 'beta': [], 'r': [], 'rti': []}
+Pm, y = matrix(P), matrix(0.0, (0, 1))
+def step():
+    f = factor(W, Pm)
+    for _ in range(2):
+        f(matrix(rng.standard_normal(n)), y, matrix(rng.standard_normal(m)))
+step()
+t0 = time.perf_counter(); k = 0
+while k < 2 or (time.perf_counter() - t0 < 10.0 and k < 20):
+    step(); k += 1
+print(json.dumps({'ms': (time.perf_counter() - t0) / k * 1e3, 'steps': k}))
+""" % (ref_dir, ROOT, args.n, args.m, args.seed)
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OPENBLAS_NUM_THREADS=str(min(cores, 64)))
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                             timeout=600)
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:   # noqa: BLE001
+        return {"value": None, "unit": "GF/s", "cores": min(cores, 64), "kind": "reference",
+                "sample": "failed: %s" % e}
+    _, _, f_it = flops(args.n, args.m)
+    return {"value": f_it / (res["ms"] * 1e-3) * 1e-9, "unit": "GF/s", "cores": min(cores, 64),
+            "kind": "reference", "ms_per_step": res["ms"],
+            "sample": "%d full-size steps (n=%d, m=%d) after 1 warm-up, reference misc.kkt_chol on "
+                      "scipy-openblas, %d threads" % (res["steps"], args.n, args.m, min(cores, 64))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--m", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.m <= 0:
+        args.m = 2 * args.n
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import cvxopt_b200
+    from cvxopt_b200 import _lib
+    if not torch.cuda.is_available() or cvxopt_b200.device_count() == 0:
+        raise RuntimeError("bench.py needs a B200: no CUDA device visible (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, m = args.n, args.m
+    f_fac, f_sol, f_it = flops(n, m)
+    P, G, d, rng = make_problem(n, m, args.seed + rank)
+    dims = {"l": m, "q": [], "s": []}
+    kkt = cvxopt_b200.kkt_chol(G, dims, None, H=P, device=local_rank)
+
+    # ---------------- device-resident arm (value) ----------------
+    dev = torch.device("cuda", local_rank)
+    d_d = torch.from_numpy(d).to(dev)
+    d_di = torch.from_numpy(1.0 / d).to(dev)
+    xs = [torch.from_numpy(rng.standard_normal(n)).to(dev) for _ in range(2)]
+    zs = [torch.from_numpy(rng.standard_normal(m)).to(dev) for _ in range(2)]
+    xw, zw = torch.empty_like(xs[0]), torch.empty_like(zs[0])
+
+    def step_dev():
+        kkt.factor_ptr(d=d_d.data_ptr(), di=d_di.data_ptr(), space=_lib.DEVICE)
+        for i in range(2):
+            xw.copy_(xs[i]); zw.copy_(zs[i])
+            torch.cuda.current_stream().synchronize()
+            kkt.solve_ptr(xw.data_ptr(), zw.data_ptr(), space=_lib.DEVICE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    syrk_ms, potrf_ms, fac_ms, sol_ms = [], [], [], []
+    barrier()
+    launches0 = cvxopt_b200.launch_count()
+    with ClockSampler(local_rank) as clk:
+        kkt.timer_start()
+        for _ in range(args.steps):
+            step_dev()
+            b = kkt.last_breakdown()
+            syrk_ms.append(b["syrk_ms"]); potrf_ms.append(b["potrf_ms"])
+            f, s = kkt.last_ms()
+            fac_ms.append(f); sol_ms.append(s)
+        total_ms = kkt.timer_stop()
+    launches = cvxopt_b200.launch_count() - launches0
+    barrier()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * f_it / (ms_step * 1e-3) * 1e-9
+
+    # ---------------- end-to-end arm (host buffers through the plugin API) ----------------
+    def pinned(a):
+        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return tt, tt.numpy()
+    keep = []
+    h_d = pinned(d); h_di = pinned(1.0 / d)
+    keep += [h_d, h_di]
+    W = {"d": h_d[1], "di": h_di[1], "v": [], "beta": [], "r": [], "rti": []}
+    hx = [pinned(rng.standard_normal(n)) for _ in range(2)]
+    hz = [pinned(rng.standard_normal(m)) for _ in range(2)]
+    hxw, hzw = pinned(np.zeros(n)), pinned(np.zeros(m))
+
+    def step_e2e():
+        solve = kkt(W)                       # f = kktsolver(W)
+        for i in range(2):
+            hxw[1][:] = hx[i][1]; hzw[1][:] = hz[i][1]
+            solve(hxw[1], None, hzw[1])      # f(x, y, z), in place on host buffers
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_val = world * f_it / (e2e_ms * 1e-3) * 1e-9
+    h2d = 2 * m * 8 + 2 * (n + m) * 8
+    d2h = 2 * (n + m) * 8
+
+    if rank == 0:
+        syrk = float(np.mean(syrk_ms))
+        f_syrk = float(n) * n * m
+        achieved = f_syrk / (syrk * 1e-3) * 1e-12
+        out = {
+            "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "dense QP KKT step n=%d m=%d ('l' cone): 1 factor + 2 solves" % (n, m),
+                       "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (G = %.2f GB, K = %.2f GB)" % (8.0 * n * m / 1e9, 8.0 * n * n / 1e9),
+                       "flops_per_step": f_it},
+            "e2e": {"value": e2e_val, "unit": "GF/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+            "breakdown_ms": {"factor": float(np.mean(fac_ms)), "syrk": syrk, "potrf": float(np.mean(potrf_ms)),
+                             "solve_each": float(np.mean(sol_ms))},
+            "ipm_iters_per_s_kkt_bound": 1e3 / ms_step,
+            "roofline": {"kernel": "dmma_gemm_kernel<XK,YK,VEC> (fused NT-scaled SYRK)", "bound": "tensor",
+                         "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
+                         "peak_source": "measured DMMA.8x8x4 pipe rate on this pool (tools/fp64_peak.cu; "
+                                        "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 = 35.4)",
+                         "traffic": None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample(args, P, G, d)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,7 +74,7 @@ struct cvxb_kkt {
     size_t swork_doubles = 0;
     CholWork cw;
     cudaStream_t st = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, t0 = nullptr, t1 = nullptr;
     double factor_ms = 0, solve_ms = 0, br[3] = {0, 0, 0};
     bool factored = false;
 };
@@ -162,6 +162,7 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     KCUDA(cudaStreamCreateWithFlags(&k->st, cudaStreamNonBlocking));
     KCUDA(cudaEventCreate(&k->e0)); KCUDA(cudaEventCreate(&k->e1));
     KCUDA(cudaEventCreate(&k->e2)); KCUDA(cudaEventCreate(&k->e3));
+    KCUDA(cudaEventCreate(&k->t0)); KCUDA(cudaEventCreate(&k->t1));
     KTRY(chol_work_create(k->cw));
     const size_t nn = (size_t)(n > 0 ? n : 1);
     if (space == CVXB_DEVICE) {
@@ -221,7 +222,7 @@ void cvxb_kkt_destroy(cvxb_kkt *k) {
     k->W.destroy();
     k->cone.destroy();
     chol_work_destroy(k->cw);
-    cudaEvent_t evs[] = {k->e0, k->e1, k->e2, k->e3};
+    cudaEvent_t evs[] = {k->e0, k->e1, k->e2, k->e3, k->t0, k->t1};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (k->st) cudaStreamDestroy(k->st);
     delete k;
@@ -417,6 +418,23 @@ int cvxb_kkt_last_ms(cvxb_kkt *k, double *factor_ms, double *solve_ms) {
     if (!k) return CVXB_E_ARG;
     if (factor_ms) *factor_ms = k->factor_ms;
     if (solve_ms) *solve_ms = k->solve_ms;
+    return 0;
+}
+int cvxb_kkt_timer_start(cvxb_kkt *k) {
+    if (!k) return CVXB_E_ARG;
+    CVXB_CUDA(cudaSetDevice(k->device));
+    CVXB_CUDA(cudaStreamSynchronize(k->st));
+    CVXB_CUDA(cudaEventRecord(k->t0, k->st));
+    return 0;
+}
+int cvxb_kkt_timer_stop(cvxb_kkt *k, double *ms) {
+    if (!k || !ms) return CVXB_E_ARG;
+    CVXB_CUDA(cudaSetDevice(k->device));
+    CVXB_CUDA(cudaEventRecord(k->t1, k->st));
+    CVXB_CUDA(cudaEventSynchronize(k->t1));
+    float t = 0;
+    CVXB_CUDA(cudaEventElapsedTime(&t, k->t0, k->t1));
+    *ms = t;
     return 0;
 }
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3) {

@@ -215,6 +215,27 @@ class KKTChol:
                                        float(beta), _lib.HOST)
         _lib.check(rc, "P operator")
 
+    # -- raw-pointer entry points (device-resident callers: bench.py, the device IPM) ----
+    def factor_ptr(self, d=0, di=0, v=0, beta=0, r=0, rti=0, dnl=0, dnli=0, H=0, ldh=1,
+                   use_resident_H=True, space=_lib.DEVICE):
+        """cvxb_kkt_factor with raw addresses (ints) living in `space`."""
+        sc = _lib.Scaling(dnl or None, dnli or None, d or None, di or None, v or None,
+                          beta or None, r or None, rti or None)
+        rc = self._lib.cvxb_kkt_factor(self._h, C.byref(sc), H or None, ldh, None, 1,
+                                       1 if use_resident_H else 0, space)
+        _lib.check(rc, "factor")
+
+    def solve_ptr(self, x, z, y=0, space=_lib.DEVICE):
+        _lib.check(self._lib.cvxb_kkt_solve(self._h, x, y or None, z, space), "solve")
+
+    def timer_start(self):
+        _lib.check(self._lib.cvxb_kkt_timer_start(self._h), "timer")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        _lib.check(self._lib.cvxb_kkt_timer_stop(self._h, C.byref(ms)), "timer")
+        return ms.value
+
     # -- introspection ---------------------------------------------------------
     def last_ms(self):
         f, s = C.c_double(), C.c_double()

@@ -104,6 +104,10 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space);
 int cvxb_kkt_get_L(cvxb_kkt *k, double *L_host, int ldl);
 /* timing of the last factor/solve in ms (CUDA events on the library stream) */
 int cvxb_kkt_last_ms(cvxb_kkt *k, double *factor_ms, double *solve_ms);
+/* bracket a timed region with CUDA events on the library's launch stream (bench.py):
+ * start records an event; stop records, synchronises and returns the elapsed ms */
+int cvxb_kkt_timer_start(cvxb_kkt *k);
+int cvxb_kkt_timer_stop(cvxb_kkt *k, double *ms);
 /* per-kernel-class CUDA-event breakdown of the last factor (syrk, potrf, scale) */
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3);
 
