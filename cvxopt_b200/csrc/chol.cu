@@ -22,103 +22,252 @@ namespace cvxb {
 
 namespace {
 
-constexpr int LDS = NB + 1;            // shared-memory leading dimension of the block
-constexpr int POTF2_SMEM = (NB * LDS + 64 * 64 + NB) * 8;
+constexpr int PB = 8;                  // inner block width of the in-CTA factorisation
+constexpr int SP = 12;                 // row stride (doubles) of the panel buffer: conflict-free frags
+constexpr int LDM = NB + 4;            // column stride (doubles) of the shared-memory block
+constexpr int POTF2_SMEM = (NB * LDM + NB * SP + 4 * 80) * 8;
 
 // Factor the jb x jb diagonal block at A (lower) in place, write inv(L) (NB x NB,
 // ld NB, zero upper, identity padding beyond jb) to inv.
+//
+// The 128x128 block lives in REGISTERS as DMMA accumulator fragments (64 doubles per
+// thread, same 8-warp 64x32 layout as the GEMM).  Right-looking with an 8-wide inner
+// block: the owning warps drop the current 128x8 column block into shared memory,
+// every warp re-derives the 8x8 Cholesky factor with shuffles (no CTA barrier for it),
+// 128 row-threads do the 8-step substitution, then all warps apply the rank-8 update to
+// their fragments with two DMMA k-steps per tile.  The inverse is then built in shared
+// memory by recursive doubling (X21 = -X22 (L21 X11)) with DMMA tile products.
 __global__ void __launch_bounds__(256, 1)
-potf2_inv_kernel(double *A, long long lda, int jb, double *inv, int *info, int joff) {
+potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, int *info, int joff) {
     extern __shared__ __align__(16) double sm[];
-    double *As = sm;                   // NB x LDS, column-major
-    double *T = As + NB * LDS;         // 64*64 temp for the inversion
-    double *colj = T + 64 * 64;        // NB
+    double *M = sm;                    // NB x LDM, column-major
+    double *P = M + NB * LDM;          // NB x SP, row-major panel
+    double *Dw = P + NB * SP;          // 4 private copies of the 8x8 factor (+ reciprocal diagonal)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp & 1, wc = warp >> 1;
+    const int g4 = lane >> 2, t4 = lane & 3;
 
     for (int e = tid; e < NB * NB; e += 256) {
         int i = e & (NB - 1), k = e >> 7;
         double v = (i == k) ? 1.0 : 0.0;
         if (i < jb && k < jb && i >= k) v = A[i + (long long)k * lda];
-        As[i + k * LDS] = v;
+        M[i + k * LDM] = v;
     }
+    __syncthreads();
+    double acc[4][8][2];
+#pragma unroll
+    for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+        for (int rf = 0; rf < 8; ++rf)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                acc[cf][rf][e] = M[(wr * 64 + rf * 8 + t4 * 2 + e) + (wc * 32 + cf * 8 + g4) * LDM];
     __syncthreads();
 
-    // ---- phase 1: unblocked right-looking Cholesky in shared memory ----
-    for (int j = 0; j < jb; ++j) {
-        const double ajj = As[j + j * LDS];
-        if (!(ajj > 0.0)) {            // also catches NaN; uniform across the CTA
-            if (tid == 0) atomicCAS(info, 0, joff + j + 1);
-            break;
-        }
-        const double s = sqrt(ajj);
-        const double rs = 1.0 / s;
-        for (int i = j + tid; i < jb; i += 256) {
-            double v = (i == j) ? s : As[i + j * LDS] * rs;
-            colj[i] = v;
-            As[i + j * LDS] = v;
-        }
-        __syncthreads();
-        for (int k = j + 1 + warp; k < jb; k += 8) {
-            const double lkj = colj[k];
-            for (int i = k + lane; i < jb; i += 32) As[i + k * LDS] -= colj[i] * lkj;
+    for (int tq = 0; tq < NB / PB / 4; ++tq) {
+#pragma unroll
+      for (int tc = 0; tc < 4; ++tc) {     // tc is compile-time: fragment indices stay static
+        const int t = tq * 4 + tc;
+        const int c0 = t * PB;
+        // 1. owners of column block t publish it: P[r][k] = C[r, c0 + k]
+        if (wc == tq) {
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    P[(wr * 64 + rf * 8 + t4 * 2 + e) * SP + g4] = acc[tc][rf][e];
         }
         __syncthreads();
+        // 2. 8x8 Cholesky of the diagonal block, redundantly in every warp.
+        //    lane -> row i = lane&7, columns 2g, 2g+1 with g = lane>>3
+        {
+            const int i = lane & 7, g = lane >> 3;
+            double d0 = P[(c0 + i) * SP + 2 * g], d1 = P[(c0 + i) * SP + 2 * g + 1];
+            double rdiag = 0.0;    // lane j keeps 1/l_jj
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                const int gj = j >> 1;
+                const double colv = (j & 1) ? d1 : d0;            // column j lives in group gj
+                const double piv = __shfl_sync(0xffffffffu, colv, j + 8 * gj);
+                if (!(piv > 0.0)) {
+                    if (!bad && tid == 0) atomicCAS(info, 0, joff + c0 + j + 1);
+                    bad = true;
+                }
+                const double s = sqrt(piv), rs = 1.0 / s;
+                if (lane == j) rdiag = rs;
+                double lij = __shfl_sync(0xffffffffu, colv, i + 8 * gj) * rs;
+                const double lk0 = __shfl_sync(0xffffffffu, colv, 2 * g + 8 * gj) * rs;
+                const double lk1 = __shfl_sync(0xffffffffu, colv, 2 * g + 1 + 8 * gj) * rs;
+                if (i == j) lij = s;
+                if (g == gj) {                                    // final column j
+                    if (j & 1) d1 = lij; else d0 = lij;
+                }
+                if (2 * g > j) d0 -= lij * lk0;
+                if (2 * g + 1 > j) d1 -= lij * lk1;
+            }
+            if (warp < 4) {
+                double *D = Dw + warp * 80;
+                D[i * 8 + 2 * g] = d0;
+                D[i * 8 + 2 * g + 1] = d1;
+                if (lane < 8) D[64 + lane] = rdiag;
+            }
+            __syncwarp();
+        }
+        // 3. substitution on the rows below (one row per thread), zero rows above
+        if (warp < 4) {
+            const double *D = Dw + warp * 80;
+            const int r = warp * 32 + lane;
+            double x[PB];
+            if (r >= c0 + PB) {
+#pragma unroll
+                for (int j = 0; j < PB; ++j) x[j] = P[r * SP + j];
+#pragma unroll
+                for (int j = 0; j < PB; ++j) {
+                    double v = x[j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) v -= x[k] * D[j * 8 + k];
+                    x[j] = v * D[64 + j];
+                }
+            } else if (r >= c0) {
+#pragma unroll
+                for (int j = 0; j < PB; ++j) x[j] = (j <= r - c0) ? D[(r - c0) * 8 + j] : 0.0;
+            } else {
+#pragma unroll
+                for (int j = 0; j < PB; ++j) x[j] = 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < PB; ++j) P[r * SP + j] = x[j];
+        }
+        __syncthreads();
+        // 4. rank-8 update of the fragments right/below the block: C -= P P'
+        {
+            double a[4][2], bfr[8][2];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                for (int cf = 0; cf < 4; ++cf) a[cf][kk] = -P[(wc * 32 + cf * 8 + g4) * SP + kk * 4 + t4];
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) bfr[rf][kk] = P[(wr * 64 + rf * 8 + g4) * SP + kk * 4 + t4];
+            }
+#pragma unroll
+            for (int cf = 0; cf < 4; ++cf) {
+                if (wc * 4 + cf <= t) continue;            // column block already final
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) {
+                    if (wr * 8 + rf <= t) continue;        // rows at/above the diagonal block
+                    dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf][0], bfr[rf][0]);
+                    dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf][1], bfr[rf][1]);
+                }
+            }
+        }
+        // 5. the finished column block of L goes to shared M and to global memory
+        for (int e = tid; e < NB * PB; e += 256) {
+            const int r = e & (NB - 1), j = e >> 7;
+            const double v = P[r * SP + j];
+            M[r + (c0 + j) * LDM] = v;
+            if (r >= c0 + j && r < jb && c0 + j < jb) A[r + (long long)(c0 + j) * lda] = v;
+        }
+        __syncthreads();
+      }
     }
-    __syncthreads();
-    // write L back (lower part only)
-    for (int e = tid; e < NB * NB; e += 256) {
-        int i = e & (NB - 1), k = e >> 7;
-        if (i < jb && k < jb && i >= k) A[i + (long long)k * lda] = As[i + k * LDS];
-    }
-    __syncthreads();
 
-    // ---- phase 2: in-place inversion by recursive doubling ----
-    // level s: for every aligned pair of s x s diagonal blocks (already inverted),
-    //   X21 = - X22 * (L21 * X11)
-    for (int i = tid; i < NB; i += 256) As[i + i * LDS] = 1.0 / As[i + i * LDS];
+    // ---- inverse of L in shared memory ----
+    // base: the 16 8x8 diagonal blocks, one per half-warp; lane (lane&15) < 8 owns column j
+    {
+        const int blk = warp * 2 + (lane >> 4);
+        const int j = lane & 15;
+        const int o = blk * PB;
+        double x[PB];
+        if (j < PB) {
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                double v = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k)
+                    if (k >= j) v -= M[(o + i) + (o + k) * LDM] * x[k];
+                x[i] = (i >= j) ? v / M[(o + i) + (o + i) * LDM] : 0.0;
+            }
+        }
+        __syncwarp();
+        if (j < PB) {
+#pragma unroll
+            for (int i = 0; i < PB; ++i) M[(o + i) + (o + j) * LDM] = x[i];
+        }
+    }
     __syncthreads();
-    for (int s = 1; s < NB; s <<= 1) {
+    for (int s = PB; s < NB; s <<= 1) {
+        const int sb = s / PB;                   // 8-blocks per side
+        const int tp = sb * sb;                  // tiles per pair
         const int npairs = NB / (2 * s);
-        const int per = s * s;
-        // T = L21 * X11   (X11 lower triangular)
-        for (int e = tid; e < npairs * per; e += 256) {
-            int pr = e / per, loc = e - pr * per;
-            int i = loc % s, jj = loc / s;
-            int o = pr * 2 * s;
-            double acc = 0.0;
-            for (int k = jj; k < s; ++k)
-                acc += As[(o + s + i) + (o + k) * LDS] * As[(o + k) + (o + jj) * LDS];
-            T[pr * per + loc] = acc;
+        // T = L21 * X11  -> stored in the (unused) upper block of the pair
+        for (int idx = warp; idx < npairs * tp; idx += 8) {
+            const int pr = idx / tp, loc = idx - pr * tp;
+            const int ti = loc % sb, tj = loc / sb;
+            const int o = pr * 2 * s;
+            double c0v = 0.0, c1v = 0.0;
+            for (int kb = tj; kb < sb; ++kb) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int k = o + kb * 8 + kk * 4 + t4;
+                    const double af = M[(o + s + ti * 8 + g4) + k * LDM];
+                    const double bf = M[k + (o + tj * 8 + g4) * LDM];
+                    dmma(c0v, c1v, af, bf);
+                }
+            }
+            M[(o + ti * 8 + g4) + (o + s + tj * 8 + t4 * 2) * LDM] = c0v;
+            M[(o + ti * 8 + g4) + (o + s + tj * 8 + t4 * 2 + 1) * LDM] = c1v;
         }
         __syncthreads();
-        // X21 = - X22 * T   (X22 lower triangular)
-        for (int e = tid; e < npairs * per; e += 256) {
-            int pr = e / per, loc = e - pr * per;
-            int i = loc % s, jj = loc / s;
-            int o = pr * 2 * s;
-            double acc = 0.0;
-            for (int k = 0; k <= i; ++k)
-                acc += As[(o + s + i) + (o + s + k) * LDS] * T[pr * per + k + jj * s];
-            As[(o + s + i) + (o + jj) * LDS] = -acc;
+        // X21 = - X22 * T
+        for (int idx = warp; idx < npairs * tp; idx += 8) {
+            const int pr = idx / tp, loc = idx - pr * tp;
+            const int ti = loc % sb, tj = loc / sb;
+            const int o = pr * 2 * s;
+            double c0v = 0.0, c1v = 0.0;
+            for (int kb = 0; kb <= ti; ++kb) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int k = kb * 8 + kk * 4 + t4;
+                    const double af = M[(o + s + ti * 8 + g4) + (o + s + k) * LDM];
+                    const double bf = M[(o + k) + (o + s + tj * 8 + g4) * LDM];
+                    dmma(c0v, c1v, af, bf);
+                }
+            }
+            M[(o + s + ti * 8 + g4) + (o + tj * 8 + t4 * 2) * LDM] = -c0v;
+            M[(o + s + ti * 8 + g4) + (o + tj * 8 + t4 * 2 + 1) * LDM] = -c1v;
         }
         __syncthreads();
     }
     for (int e = tid; e < NB * NB; e += 256) {
         int i = e & (NB - 1), k = e >> 7;
-        inv[e] = (i >= k) ? As[i + k * LDS] : 0.0;
+        inv[e] = (i >= k) ? M[i + k * LDM] : 0.0;
+        invT[e] = (k >= i) ? M[k + i * LDM] : 0.0;     // invT[i + k*NB] = inv[k + i*NB]
     }
 }
 
 // ---- blocked triangular solve with one right-hand side ------------------------
-// forward:  L x = b ;  backward: L' x = b.   In place on b.  One CTA per row block.
+// forward:  L x = b ;  backward: L' x = b.   In place on b.  One CTA per 128-row block.
 // flags[i] == epoch  <=>  x_i is final in b.
-template <bool TRANS>
+//
+// CTA `bi` streams its block row (forward) / block column (backward) of L through a
+// cp.async ring of 128x32 chunks that runs ahead of the dependency chain (L is static,
+// only x arrives late), keeps inv(L_ii) in registers, and waits on the flag of block j
+// only when it reaches that block's columns.  The critical path per block is then
+// flag -> 128x128 smem GEMV -> 128x128 register GEMV -> flag.
+constexpr int TR_CH = 32;                       // columns per ring chunk
+constexpr int TR_R = 5;                         // ring depth
+constexpr int TRSV_SMEM = (TR_R * NB * TR_CH + 4 * NB) * 8;
+
+template <bool TRANS, bool VEC>
 __global__ void __launch_bounds__(256, 1)
 trsv_kernel(int n, const double *__restrict__ L, long long ldl, const double *__restrict__ inv,
-            double *b, int *flags, int epoch) {
-    __shared__ double xs[NB];
-    __shared__ double part[2][NB];
-    __shared__ double tvec[NB];
+            const double *__restrict__ invT, double *b, int *flags, int epoch) {
+    extern __shared__ __align__(16) double sm[];
+    double *ring = sm;                          // TR_R x (32 cols x 128 rows), column-contiguous
+    double *xs = ring + TR_R * NB * TR_CH;      // 128
+    double *part = xs + NB;                     // 2 x 128
+    double *tvec = part + 2 * NB;               // 128
     const int nblk = (n + NB - 1) / NB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bi = TRANS ? (nblk - 1 - (int)blockIdx.x) : (int)blockIdx.x;
@@ -126,85 +275,111 @@ trsv_kernel(int n, const double *__restrict__ L, long long ldl, const double *__
     const int ni = min(NB, n - i0);
     const int r = tid & (NB - 1), half = tid >> 7;
 
-    double acc = 0.0;
-    if (!TRANS) {
-        for (int j = 0; j < bi; ++j) {
-            if (tid == 0) while (ld_acquire(flags + j) != epoch) { }
-            __syncthreads();
-            if (tid < NB) xs[tid] = __ldcg(b + j * NB + tid);
-            __syncthreads();
-            if (r < ni) {
-                const double *Lp = L + (i0 + r) + (long long)(j * NB + half * 64) * ldl;
-#pragma unroll 8
-                for (int c = 0; c < 64; ++c) acc += Lp[(long long)c * ldl] * xs[half * 64 + c];
+    // inverse of the diagonal block -> registers (row r of inv, or row r of inv' for TRANS)
+    double ireg[64];
+    {
+        const double *ip = (TRANS ? invT : inv) + (long long)bi * NB * NB + r + (long long)(half * 64) * NB;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) ireg[k] = ip[k * NB];
+    }
+
+    const int nb_dep = TRANS ? (nblk - 1 - bi) : bi;         // blocks this CTA depends on
+    const int nchunks = nb_dep * (NB / TR_CH);
+    // chunk q -> (block j, column chunk cc)
+    auto issue = [&](int q) {
+        const int jj = q / (NB / TR_CH), cc = q % (NB / TR_CH);
+        const int j = TRANS ? (nblk - 1 - jj) : jj;
+        double *dst = ring + (q % TR_R) * (NB * TR_CH);
+        const double *src;
+        int nrows, ncols;
+        if (!TRANS) { src = L + i0 + (long long)(j * NB + cc * TR_CH) * ldl; nrows = ni; ncols = TR_CH; }
+        else { src = L + (long long)j * NB + (long long)(i0 + cc * TR_CH) * ldl; nrows = min(NB, n - j * NB); ncols = min(TR_CH, ni - cc * TR_CH); }
+        if (VEC) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int e = tid + it * 256;          // 2048 16-byte pieces
+                const int c = e >> 6, rr = (e & 63) * 2;
+                const int rem = nrows - rr;
+                const int bytes = (c < ncols) ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
+                cp_async16(dst + c * NB + rr, bytes ? (src + rr + (long long)c * ldl) : L, bytes);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int e = tid + it * 256;
+                const int c = e >> 7, rr = e & 127;
+                const int bytes = (c < ncols && rr < nrows) ? 8 : 0;
+                cp_async8(dst + c * NB + rr, bytes ? (src + rr + (long long)c * ldl) : L, bytes);
             }
         }
-        part[half][r] = acc;
+    };
+#pragma unroll
+    for (int q = 0; q < TR_R - 1; ++q) {
+        if (q < nchunks) issue(q);
+        cp_async_commit();
+    }
+
+    double acc = 0.0;           // forward: partial of row r over this thread's columns
+    double accc[16];            // backward: per-lane partials of the warp's 16 columns
+#pragma unroll
+    for (int q = 0; q < 16; ++q) accc[q] = 0.0;
+
+    for (int jj = 0; jj < nb_dep; ++jj) {
+        const int j = TRANS ? (nblk - 1 - jj) : jj;
+        if (tid == 0) while (ld_acquire(flags + j) != epoch) { }
         __syncthreads();
-        if (tid < NB) tvec[tid] = (tid < ni) ? (__ldcg(b + i0 + tid) - part[0][tid] - part[1][tid]) : 0.0;
-        __syncthreads();
-        // x_i = inv_ii * t   (inv lower: columns c <= r)
-        double a2 = 0.0;
-        {
-            const double *ip = inv + (long long)bi * NB * NB + r + (long long)(half * 64) * NB;
-            for (int c = 0; c < 64; ++c) {
-                int cc = half * 64 + c;
-                if (cc <= r) a2 += ip[c * NB] * tvec[cc];
+        if (tid < NB) xs[tid] = (j * NB + tid < n) ? __ldcg(b + j * NB + tid) : 0.0;
+#pragma unroll
+        for (int cc = 0; cc < NB / TR_CH; ++cc) {
+            const int q = jj * (NB / TR_CH) + cc;
+            cp_async_wait<TR_R - 2>();
+            __syncthreads();
+            {
+                const int nq = q + TR_R - 1;
+                if (nq < nchunks) issue(nq);
+                cp_async_commit();
             }
-        }
-        __syncthreads();
-        part[half][r] = a2;
-        __syncthreads();
-        if (tid < ni) b[i0 + tid] = part[0][tid] + part[1][tid];
-    } else {
-        // accumulate t[c] = sum_{j>bi} sum_r L[j*NB + r, i0 + c] * x_j[r]; warp w owns
-        // columns c = w*16 .. w*16+15
-        double accc[16];
+            const double *ch = ring + (q % TR_R) * (NB * TR_CH);
+            if (!TRANS) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) accc[q] = 0.0;
-        for (int j = nblk - 1; j > bi; --j) {
-            if (tid == 0) while (ld_acquire(flags + j) != epoch) { }
-            __syncthreads();
-            const int nj = min(NB, n - j * NB);
-            if (tid < NB) xs[tid] = (tid < nj) ? __ldcg(b + j * NB + tid) : 0.0;
-            __syncthreads();
+                for (int c = 0; c < 16; ++c)
+                    acc += ch[(half * 16 + c) * NB + r] * xs[cc * TR_CH + half * 16 + c];
+            } else {
+                // warp w owns chunk columns w*4 .. w*4+3; lanes stride the 128 rows
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                int c = warp * 16 + q;
-                if (c < ni) {
-                    const double *Lp = L + (long long)(j * NB) + (long long)(i0 + c) * ldl;
+                for (int qc = 0; qc < 4; ++qc) {
+                    const double *col = ch + (warp * 4 + qc) * NB;
                     double a = 0.0;
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        int row = lane + rr * 32;
-                        if (row < nj) a += Lp[row] * xs[row];
-                    }
-                    accc[q] += a;
+                    for (int rr = 0; rr < 4; ++rr) a += col[lane + rr * 32] * xs[lane + rr * 32];
+                    accc[cc * 4 + qc] += a;
                 }
             }
         }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (!TRANS) {
+        part[half * NB + r] = acc;
+        __syncthreads();
+        if (tid < NB) tvec[tid] = (tid < ni) ? (b[i0 + tid] - part[tid] - part[NB + tid]) : 0.0;
+        __syncthreads();
+    } else {
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            double a = warp_sum(accc[q]);
-            int c = warp * 16 + q;
-            if (lane == 0) tvec[c] = (c < ni) ? (__ldcg(b + i0 + c) - a) : 0.0;
+            const double a = warp_sum(accc[q]);
+            const int c = (q >> 2) * TR_CH + warp * 4 + (q & 3);
+            if (lane == 0) tvec[c] = (c < ni) ? (b[i0 + c] - a) : 0.0;
         }
         __syncthreads();
-        // x_i[c] = sum_{r >= c} inv[r, c] * t[r]
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            int c = warp * 16 + q;
-            const double *ip = inv + (long long)bi * NB * NB + (long long)c * NB;
-            double a = 0.0;
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                int row = lane + rr * 32;
-                if (row >= c) a += ip[row] * tvec[row];
-            }
-            a = warp_sum(a);
-            if (lane == 0 && c < ni) b[i0 + c] = a;
-        }
     }
+    // x_i = inv_ii * t  (forward)  /  inv_ii' * t (backward): row r of the (transposed) inverse
+    double a2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) a2 += ireg[k] * tvec[half * 64 + k];
+    part[half * NB + r] = a2;
+    __syncthreads();
+    if (tid < ni) b[i0 + tid] = part[tid] + part[NB + tid];
     __threadfence();
     __syncthreads();
     if (tid == 0) st_release(flags + bi, epoch);
@@ -228,9 +403,13 @@ int chol_work_create(CholWork &w) {
     CVXB_CUDA(cudaMemset(w.d_info, 0, sizeof(int)));
     CVXB_CUDA(cudaMalloc(&w.d_flags, 4096 * sizeof(int)));
     CVXB_CUDA(cudaMemset(w.d_flags, 0, 4096 * sizeof(int)));
-    CVXB_CUDA(cudaMalloc(&w.splitk_ws, (size_t)kNumSMs * NB * NB * sizeof(double)));
+    CVXB_CUDA(cudaMalloc(&w.splitk_ws, dmma_gemm_splitk_ws_doubles() * sizeof(double)));
     CVXB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    POTF2_SMEM));
+    CVXB_CUDA(cudaFuncSetAttribute(trsv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CVXB_CUDA(cudaFuncSetAttribute(trsv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CVXB_CUDA(cudaFuncSetAttribute(trsv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    CVXB_CUDA(cudaFuncSetAttribute(trsv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
     return 0;
 }
 
@@ -245,12 +424,25 @@ void chol_work_destroy(CholWork &w) {
     if (w.d_info) cudaFree(w.d_info);
     if (w.d_flags) cudaFree(w.d_flags);
     if (w.splitk_ws) cudaFree(w.splitk_ws);
+    if (w.panel[0]) cudaFree(w.panel[0]);
+    if (w.panel[1]) cudaFree(w.panel[1]);
     w = CholWork();
 }
 
 int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_t st) {
     if (n <= 0) return 0;
     const int nblk = (n + NB - 1) / NB;
+    if (w.panel_rows < n) {
+        for (int i = 0; i < 2; ++i) {
+            if (w.panel[i]) CVXB_CUDA(cudaFree(w.panel[i]));
+            w.panel[i] = nullptr;
+        }
+        const int rows = (n + 1) & ~1;
+        for (int i = 0; i < 2; ++i) CVXB_CUDA(cudaMalloc(&w.panel[i], (size_t)rows * NB * sizeof(double)));
+        w.panel_rows = rows;
+    }
+    const int ldw = w.panel_rows;
+    const int panel_tiles = NB / dmma_gemm_tile_cols();      // c tiles that make up the next panel
     cudaStream_t P = w.panel_stream, U = w.update_stream;
     CVXB_CUDA(cudaMemsetAsync(w.d_info, 0, sizeof(int), st));
     CVXB_CUDA(cudaEventRecord(w.ev_start, st));
@@ -263,38 +455,44 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
         const int m = n - j - wj;
         double *Ajj = A + j + (long long)j * lda;
         double *invj = inv + (long long)jb * NB * NB;
-        potf2_inv_kernel<<<1, 256, POTF2_SMEM, P>>>(Ajj, lda, wj, invj, w.d_info, j);
+        double *invTj = inv + (long long)(nblk + jb) * NB * NB;
+        potf2_inv_kernel<<<1, 256, POTF2_SMEM, P>>>(Ajj, lda, wj, invj, invTj, w.d_info, j);
         count_launch();
         CVXB_LAUNCH_CHECK();
         if (m <= 0) break;
         double *A21 = Ajj + wj;
         double *A22 = A21 + (long long)wj * lda;
-        {   // panel TRSM as GEMM with the block inverse (in place: one CTA owns its rows)
+        double *Wp = w.panel[jb & 1];
+        {   // panel TRSM as a GEMM with the block inverse: Wp = A21 * inv(L11)'
+            // (out of place: the two 64-column tiles of a row block read all 128 columns)
             GemmDesc g;
             g.M = m; g.N = wj; g.K = wj;
             g.X = A21; g.ldx = lda; g.x_kmajor = false;
             g.Y = invj; g.ldy = NB; g.y_kmajor = false;
-            g.C = A21; g.ldc = lda;
+            g.C = Wp; g.ldc = ldw;
             CVXB_TRY(dmma_gemm(g, P));
         }
         CVXB_CUDA(cudaEventRecord(w.ev_panel, P));
         GemmDesc u;
         u.M = m; u.N = m; u.K = wj;
-        u.X = A21; u.ldx = lda; u.x_kmajor = false;
-        u.Y = A21; u.ldy = lda; u.y_kmajor = false;
+        u.X = Wp; u.ldx = ldw; u.x_kmajor = false;
+        u.Y = Wp; u.ldy = ldw; u.y_kmajor = false;
         u.D = A22; u.ldd = lda; u.C = A22; u.ldc = lda;
         u.alpha = -1.0; u.beta = 1.0; u.lower_only = true;
-        // tile column 0 (the next panel) on the panel stream
+        // the next panel's columns first, on the panel stream
         if (have_rest) CVXB_CUDA(cudaStreamWaitEvent(P, w.ev_rest, 0));
-        u.ct_begin = 0; u.ct_end = 1;
+        u.ct_begin = 0; u.ct_end = panel_tiles;
         CVXB_TRY(dmma_gemm(u, P));
         if (m > NB) {
             CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_panel, 0));
-            u.ct_begin = 1; u.ct_end = 1 << 30;
+            u.ct_begin = panel_tiles; u.ct_end = 1 << 30;
             CVXB_TRY(dmma_gemm(u, U));
             CVXB_CUDA(cudaEventRecord(w.ev_rest, U));
             have_rest = true;
         }
+        // L21 itself goes back into A (off the critical path of the next panel)
+        CVXB_CUDA(cudaMemcpy2DAsync(A21, (size_t)lda * sizeof(double), Wp, (size_t)ldw * sizeof(double),
+                                    (size_t)m * sizeof(double), wj, cudaMemcpyDeviceToDevice, P));
     }
     CVXB_CUDA(cudaEventRecord(w.ev_end_p, P));
     CVXB_CUDA(cudaEventRecord(w.ev_end_u, U));
@@ -312,8 +510,15 @@ int trsv_lower(int n, const double *L, int ldl, const double *inv, double *b, bo
         return CVXB_E_ARG;
     }
     const int epoch = ++g_trsv_epoch;
-    if (trans) trsv_kernel<true><<<nblk, 256, 0, st>>>(n, L, ldl, inv, b, w.d_flags, epoch);
-    else       trsv_kernel<false><<<nblk, 256, 0, st>>>(n, L, ldl, inv, b, w.d_flags, epoch);
+    const double *invT = inv + (long long)nblk * NB * NB;
+    const bool vec = ((uintptr_t)L % 16 == 0) && (ldl % 2 == 0);
+    if (trans) {
+        if (vec) trsv_kernel<true, true><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
+        else     trsv_kernel<true, false><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
+    } else {
+        if (vec) trsv_kernel<false, true><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
+        else     trsv_kernel<false, false><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
+    }
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;

@@ -107,6 +107,8 @@ struct GemmDesc {
     double *splitk_ws = nullptr;
 };
 int dmma_gemm(const GemmDesc &g, cudaStream_t st);
+size_t dmma_gemm_splitk_ws_doubles();   // workspace size for GemmDesc::splitk_ws
+int dmma_gemm_tile_cols();              // width of a c tile (units of ct_begin / ct_end)
 
 // Cholesky (lower) of the n x n matrix A in place; inv receives the inverses of the
 // NB x NB diagonal blocks of L (block j at inv + j*NB*NB, leading dimension NB).
@@ -119,6 +121,8 @@ struct CholWork {
     int *d_info = nullptr;                // device flag
     int *d_flags = nullptr;               // trsv progress flags (>= n/NB + 1 ints)
     double *splitk_ws = nullptr;
+    double *panel[2] = {nullptr, nullptr};   // out-of-place TRSM results (double-buffered)
+    int panel_rows = 0;
 };
 int chol_work_create(CholWork &w);
 void chol_work_destroy(CholWork &w);

@@ -7,34 +7,43 @@
 //     lower tiles only; replaces scale(Gs)+blas.syrk+`K += H`,   reference misc.py:1268-1276)
 //   * Cholesky panel TRSM  L21 = A21 * L11^{-T}                  (X=A21, Y=inv(L11), M-major)
 //   * Cholesky trailing update A22 -= L21 L21'                   (X=Y=L21, M-major, lower)
-//   * the 's'-cone congruences r' X r                            (general GEMMs)
+//   * the 's'-cone congruences r' X r                            (batched general GEMMs)
 //
 // B200 has no tcgen05 kind for fp64 (ptxas rejects kind::f64), so the fp64 tensor
 // path is warp-level DMMA.8x8x4 (mma.sync.m8n8k4.f64).  Measured pipe peak on this
 // pool: 37.2 TF/s = 64 FMA/clk/SM * 148 SMs * 1.965 GHz (tools/fp64_peak.cu).  At
-// 64 FMA/clk a 128x128x16 tile step keeps an SM busy for 4096 cycles while moving
-// only 32 KB, so operand traffic is trivial; the design goal is simply to keep the
-// DMMA pipe issuing: 8 warps, 64x32 warp tiles (64 accumulator doubles / thread,
-// 32 independent DMMAs between dependent ones), 4-stage cp.async pipeline, padded
-// shared-memory layouts that make every fragment LDS.64 bank-conflict free.
+// 64 FMA/clk a 128x64x16 tile step keeps the pipe busy for 2048 cycles while moving
+// 24 KB, so operand traffic is trivial; the design goal is to keep the DMMA pipe
+// issuing:
+//   * 128-thread CTAs (4 warps, 64x32 warp tiles, 64 accumulator doubles / thread),
+//     TWO CTAs per SM so one CTA's barrier / prologue / epilogue bubbles are covered
+//     by the other CTA's DMMAs (r01a profile: 21 % of the pipe idle with one CTA/SM)
+//   * 3-stage cp.async pipeline, padded shared-memory layouts that make every
+//     fragment LDS.64 bank-conflict free
+//   * fragments double-buffered in registers so the di^2 scaling DMULs of step kk+1
+//     issue before the DMMAs of step kk (no DMUL->DMMA dependency stall)
+//   * per-thread copy descriptors hoisted out of the k loop
 //
 // MMA roles are swapped w.r.t. the matrix: the MMA "m" index runs over C's columns
 // (Y operand), the "n" index over C's rows (X operand), so each thread's accumulator
-// pair is two consecutive ROWS of a column-major C (contiguous).
+// pair is two consecutive ROWS of a column-major C (one 16-byte access).
 #include "common.cuh"
 
 namespace cvxb {
 
 namespace {
 
-constexpr int BR = 128, BC = 128, BK = 16, STAGES = 4;
-constexpr int SK = BK + 4;       // row stride (doubles) of a K-major operand tile  [idx][k]
-constexpr int SMJ = BR + 4;      // row stride (doubles) of an M-major operand tile [k][idx]
-constexpr int OPER_STAGE = 128 * SK;  // 2560 doubles >= 16*132
-constexpr int STAGE_DOUBLES = 2 * OPER_STAGE + BK;
-constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+constexpr int BR = 128, BC = 64, BK = 16, STAGES = 3;
+constexpr int THREADS = 128;
+constexpr int SK = BK + 4;            // row stride (doubles) of a K-major operand tile  [idx][k]
+constexpr int SMX = BR + 4;           // row stride of an M-major X tile [k][idx]  (132 = 4 mod 16)
+constexpr int SMY = BC + 4;           // row stride of an M-major Y tile [k][idx]  (68  = 4 mod 16)
+constexpr int X_STAGE = BR * SK;      // 2560 doubles >= 16*132
+constexpr int Y_STAGE = BC * SK;      // 1280 doubles >= 16*68
+constexpr int STAGE_DOUBLES = X_STAGE + Y_STAGE + BK;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;      // 92544 B -> 2 CTAs / SM
 constexpr int TILE_ELEMS = BR * BC;
-constexpr int THREADS = 256;
+constexpr int CTAS_PER_WAVE = 2 * kNumSMs;
 
 struct KParams {
     int M, N, K;
@@ -45,27 +54,29 @@ struct KParams {
     double *C; long long ldc;
     double alpha, beta;
     int lower_only;
-    int ct_begin, ct_end;   // c-tile window (already clipped to the tile grid)
+    int ct_begin, ct_end;   // c-tile window in units of BC columns (already clipped)
     int nTr;                // number of r tiles
     long long sX, sY, sW, sD, sC;
-    // split-K
     int full_tiles;         // units [0, full_tiles) are whole tiles
     int S;                  // splits per remainder tile (1 = none)
     int kchunk;             // K elements per split (multiple of BK)
     double *ws;
+    int vec_c;              // C/D allow 16-byte accesses
 };
 
+// first r tile that intersects the lower triangle for c tile `tc`
+__device__ __host__ __forceinline__ int first_tr(int tc) { return (tc * BC) / BR; }
+
 __device__ __forceinline__ void decode_tile(const KParams &p, int t, int &tr, int &tc) {
-    // tiles are enumerated c-tile by c-tile (column-major over the tile grid)
     int c = p.ct_begin;
     if (p.lower_only) {
         while (true) {
-            int cnt = p.nTr - c;
+            int cnt = p.nTr - first_tr(c);
             if (t < cnt) break;
             t -= cnt;
             ++c;
         }
-        tr = c + t;
+        tr = first_tr(c) + t;
         tc = c;
     } else {
         tc = c + t / p.nTr;
@@ -73,60 +84,60 @@ __device__ __forceinline__ void decode_tile(const KParams &p, int t, int &tr, in
     }
 }
 
-// ---- operand tile loaders ----------------------------------------------------
-// K-major source: element (idx, k) at src[k + idx*ld]; smem [idx*SK + k]
-template <bool VEC>
-__device__ __forceinline__ void load_kmajor(double *s, const double *src, long long ld,
-                                            int nrows, int kvalid, int tid) {
-    if (VEC) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int q = tid + i * THREADS;
-            int idx = q >> 3, kc = (q & 7) * 2;
-            int rem = kvalid - kc;
-            int bytes = (idx < nrows) ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
-            const double *g = bytes ? (src + kc + (long long)idx * ld) : src;
-            cp_async16(s + idx * SK + kc, g, bytes);
+// A thread's share of one operand tile copy.  Piece i of a thread sits at a fixed stride
+// from piece 0 (rows advance for a K-major tile, k advances for an M-major tile), so the
+// plan is a base pointer, a stride and two small integers; K advances by a pointer offset.
+template <bool KMAJOR, bool VEC, int ROWS>
+struct CopyPlan {
+    static constexpr int W = VEC ? 2 : 1;                         // doubles per piece
+    static constexpr int PER = KMAJOR ? BK / W : ROWS / W;        // pieces per row / per k
+    static constexpr int NP = ROWS * BK / W / THREADS;            // pieces per thread
+    static constexpr int DSTEP = THREADS / PER;                   // row (or k) step between pieces
+    static constexpr int STRIDE_M = ROWS + 4;
+    static constexpr int SSTEP = DSTEP * (KMAJOR ? SK : STRIDE_M);
+    const double *g0;
+    long long gstep;
+    int s0, idx0, k0, cbytes;
+
+    __device__ __forceinline__ void init(const double *src, long long ld, int nrows, int tid) {
+        const int a = tid / PER, bq = (tid % PER) * W;
+        if (KMAJOR) {
+            idx0 = a; k0 = bq;
+            g0 = src + k0 + (long long)idx0 * ld;
+            s0 = idx0 * SK + k0;
+            cbytes = 8 * W;                                        // k validity of a full tile
+        } else {
+            k0 = a; idx0 = bq;
+            g0 = src + idx0 + (long long)k0 * ld;
+            s0 = k0 * STRIDE_M + idx0;
+            const int rem = nrows - idx0;
+            cbytes = rem >= W ? 8 * W : (rem > 0 ? 8 * rem : 0);   // row validity (constant)
         }
-    } else {
+        gstep = (long long)DSTEP * ld;
+    }
+    __device__ __forceinline__ void issue(double *sbase, const double *base, long long goff,
+                                          int nrows, int kvalid) const {
+        const double *g = g0 + goff;
+        int kb = cbytes;
+        if (KMAJOR && kvalid < BK) {                               // k tail (last tile only)
+            const int rem = kvalid - k0;
+            kb = rem >= W ? 8 * W : (rem > 0 ? 8 * rem : 0);
+        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int q = tid + i * THREADS;
-            int idx = q >> 4, kc = q & 15;
-            int bytes = (idx < nrows && kc < kvalid) ? 8 : 0;
-            const double *g = bytes ? (src + kc + (long long)idx * ld) : src;
-            cp_async8(s + idx * SK + kc, g, bytes);
+        for (int i = 0; i < NP; ++i) {
+            int bytes;
+            if (KMAJOR) bytes = (idx0 + i * DSTEP < nrows) ? kb : 0;
+            else        bytes = (k0 + i * DSTEP < kvalid) ? kb : 0;
+            const double *gp = bytes ? g : base;
+            if (VEC) cp_async16(sbase + s0 + i * SSTEP, gp, bytes);
+            else     cp_async8(sbase + s0 + i * SSTEP, gp, bytes);
+            g += gstep;
         }
     }
-}
-// M-major source: element (idx, k) at src[idx + k*ld]; smem [k*SMJ + idx]
-template <bool VEC>
-__device__ __forceinline__ void load_mmajor(double *s, const double *src, long long ld,
-                                            int nrows, int kvalid, int tid) {
-    if (VEC) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int q = tid + i * THREADS;
-            int k = q >> 6, ic = (q & 63) * 2;
-            int rem = nrows - ic;
-            int bytes = (k < kvalid) ? (rem >= 2 ? 16 : (rem == 1 ? 8 : 0)) : 0;
-            const double *g = bytes ? (src + ic + (long long)k * ld) : src;
-            cp_async16(s + k * SMJ + ic, g, bytes);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int q = tid + i * THREADS;
-            int k = q >> 7, ic = q & 127;
-            int bytes = (k < kvalid && ic < nrows) ? 8 : 0;
-            const double *g = bytes ? (src + ic + (long long)k * ld) : src;
-            cp_async8(s + k * SMJ + ic, g, bytes);
-        }
-    }
-}
+};
 
 template <bool XK, bool YK, bool VEC>
-__global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(const KParams p) {
+__global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wr = warp & 1, wc = warp >> 1;
@@ -156,9 +167,18 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(const KParams p) 
     const double *X = p.X + b * p.sX;
     const double *Y = p.Y + b * p.sY;
     const double *w = p.w ? p.w + b * p.sW : nullptr;
+    const bool has_w = (w != nullptr);
 
-    const double *Xt = XK ? X + (long long)r0 * p.ldx : X + r0;
-    const double *Yt = YK ? Y + (long long)c0 * p.ldy : Y + c0;
+    // tile origins at k = kbeg
+    const double *Xt = XK ? X + (long long)r0 * p.ldx + kbeg : X + r0 + (long long)kbeg * p.ldx;
+    const double *Yt = YK ? Y + (long long)c0 * p.ldy + kbeg : Y + c0 + (long long)kbeg * p.ldy;
+    const long long xstep = XK ? BK : (long long)BK * p.ldx;     // pointer advance per k tile
+    const long long ystep = YK ? BK : (long long)BK * p.ldy;
+
+    CopyPlan<XK, VEC, BR> px;
+    CopyPlan<YK, VEC, BC> py;
+    px.init(Xt, p.ldx, nr, tid);
+    py.init(Yt, p.ldy, nc, tid);
 
     double acc[4][8][2];
 #pragma unroll
@@ -170,17 +190,14 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(const KParams p) 
 
     auto load_stage = [&](int kt, int stage) {
         double *sx = smem + stage * STAGE_DOUBLES;
-        double *sy = sx + OPER_STAGE;
-        double *sw = sy + OPER_STAGE;
-        const int k0 = kbeg + kt * BK;
-        const int kvalid = min(BK, kend - k0);
-        if (XK) load_kmajor<VEC>(sx, Xt + k0, p.ldx, nr, kvalid, tid);
-        else    load_mmajor<VEC>(sx, Xt + (long long)k0 * p.ldx, p.ldx, nr, kvalid, tid);
-        if (YK) load_kmajor<VEC>(sy, Yt + k0, p.ldy, nc, kvalid, tid);
-        else    load_mmajor<VEC>(sy, Yt + (long long)k0 * p.ldy, p.ldy, nc, kvalid, tid);
-        if (w != nullptr && tid < BK) {
-            int bytes = (tid < kvalid) ? 8 : 0;
-            cp_async8(sw + tid, bytes ? (w + k0 + tid) : w, bytes);
+        double *sy = sx + X_STAGE;
+        double *sw = sy + Y_STAGE;
+        const int kvalid = min(BK, kend - kbeg - kt * BK);
+        px.issue(sx, X, (long long)kt * xstep, nr, kvalid);
+        py.issue(sy, Y, (long long)kt * ystep, nc, kvalid);
+        if (has_w && tid < BK) {
+            const int bytes = (tid < kvalid) ? 8 : 0;
+            cp_async8(sw + tid, bytes ? (w + kbeg + kt * BK + tid) : w, bytes);
         }
     };
 
@@ -190,41 +207,61 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(const KParams p) 
         cp_async_commit();
     }
 
-    const bool has_w = (w != nullptr);
+    // fragment offsets (doubles) inside a stage, for k = t4
+    int xoff[8], yoff[4];
+#pragma unroll
+    for (int rf = 0; rf < 8; ++rf) {
+        const int idx = wr * 64 + rf * 8 + g4;
+        xoff[rf] = XK ? idx * SK + t4 : t4 * SMX + idx;
+    }
+#pragma unroll
+    for (int cf = 0; cf < 4; ++cf) {
+        const int idx = wc * 32 + cf * 8 + g4;
+        yoff[cf] = X_STAGE + (YK ? idx * SK + t4 : t4 * SMY + idx);
+    }
+    constexpr int XKK = XK ? 4 : 4 * SMX;       // offset advance per kk step (4 k values)
+    constexpr int YKK = YK ? 4 : 4 * SMY;
+
     for (int kt = 0; kt < ktiles; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
+        const double *st = smem + (kt % STAGES) * STAGE_DOUBLES;
+        // fragments of kk = 0 first, so their latency overlaps the prefetch issue below
+        double a[2][4], bf[2][8];
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) a[0][cf] = st[yoff[cf]];
+#pragma unroll
+        for (int rf = 0; rf < 8; ++rf) bf[0][rf] = st[xoff[rf]];
+        double wv = 1.0;
+        if (has_w) wv = st[X_STAGE + Y_STAGE + t4];
         {
-            int nk = kt + STAGES - 1;
+            const int nk = kt + STAGES - 1;
             if (nk < ktiles) load_stage(nk, nk % STAGES);
             cp_async_commit();
         }
-        const double *sx = smem + (kt % STAGES) * STAGE_DOUBLES;
-        const double *sy = sx + OPER_STAGE;
-        const double *sw = sy + OPER_STAGE;
+        if (has_w) {
+#pragma unroll
+            for (int cf = 0; cf < 4; ++cf) a[0][cf] *= wv;
+        }
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            const int k = kk * 4 + t4;
-            double a[4], bf[8];
+            const int cur = kk & 1, nxt = cur ^ 1;
+            if (kk + 1 < BK / 4) {
 #pragma unroll
-            for (int cf = 0; cf < 4; ++cf) {
-                int idx = wc * 32 + cf * 8 + g4;
-                a[cf] = YK ? sy[idx * SK + k] : sy[k * SMJ + idx];
-            }
+                for (int cf = 0; cf < 4; ++cf) a[nxt][cf] = st[yoff[cf] + (kk + 1) * YKK];
 #pragma unroll
-            for (int rf = 0; rf < 8; ++rf) {
-                int idx = wr * 64 + rf * 8 + g4;
-                bf[rf] = XK ? sx[idx * SK + k] : sx[k * SMJ + idx];
-            }
-            if (has_w) {
-                double wv = sw[k];
+                for (int rf = 0; rf < 8; ++rf) bf[nxt][rf] = st[xoff[rf] + (kk + 1) * XKK];
+                if (has_w) {
+                    const double wn = st[X_STAGE + Y_STAGE + (kk + 1) * 4 + t4];
 #pragma unroll
-                for (int cf = 0; cf < 4; ++cf) a[cf] *= wv;
+                    for (int cf = 0; cf < 4; ++cf) a[nxt][cf] *= wn;
+                }
             }
 #pragma unroll
             for (int cf = 0; cf < 4; ++cf)
 #pragma unroll
-                for (int rf = 0; rf < 8; ++rf) dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bf[rf]);
+                for (int rf = 0; rf < 8; ++rf)
+                    dmma(acc[cf][rf][0], acc[cf][rf][1], a[cur][cf], bf[cur][rf]);
         }
     }
     cp_async_wait<0>();
@@ -236,8 +273,8 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(const KParams p) 
         for (int cf = 0; cf < 4; ++cf)
 #pragma unroll
             for (int rf = 0; rf < 8; ++rf) {
-                int rl = wr * 64 + rf * 8 + t4 * 2;
-                int cl = wc * 32 + cf * 8 + g4;
+                const int rl = wr * 64 + rf * 8 + t4 * 2;
+                const int cl = wc * 32 + cf * 8 + g4;
                 *reinterpret_cast<double2 *>(ws + rl + cl * BR) =
                     make_double2(acc[cf][rf][0], acc[cf][rf][1]);
             }
@@ -245,7 +282,30 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(const KParams p) 
     }
     double *C = p.C + b * p.sC;
     const double *D = p.D ? p.D + b * p.sD : nullptr;
-    const bool diag = p.lower_only && (tr == tc);
+    const bool diag = p.lower_only && (c0 + BC - 1 > r0);       // tile touches the diagonal
+    const bool use_d = (p.beta != 0.0);
+    const bool fast = p.vec_c && (nr == BR) && (nc == BC) && !diag;
+    if (fast) {
+        // full interior tile: 16-byte accesses, all D loads of a column group in flight together
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) {
+            const long long c = c0 + wc * 32 + cf * 8 + g4;
+            double2 dv[8];
+            if (use_d) {
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf)
+                    dv[rf] = *reinterpret_cast<const double2 *>(
+                        D + (r0 + wr * 64 + rf * 8 + t4 * 2) + c * p.ldd);
+            }
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) {
+                double2 v = make_double2(p.alpha * acc[cf][rf][0], p.alpha * acc[cf][rf][1]);
+                if (use_d) { v.x += p.beta * dv[rf].x; v.y += p.beta * dv[rf].y; }
+                *reinterpret_cast<double2 *>(C + (r0 + wr * 64 + rf * 8 + t4 * 2) + c * p.ldc) = v;
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int cf = 0; cf < 4; ++cf) {
         const int cl = wc * 32 + cf * 8 + g4;
@@ -257,32 +317,31 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(const KParams p) 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 if (rl + e >= nr) continue;
-                if (diag && (rl + e) < cl) continue;
                 const long long r = r0 + rl + e;
+                if (diag && r < c) continue;
                 double v = p.alpha * acc[cf][rf][e];
-                if (p.beta != 0.0) v += p.beta * D[r + c * p.ldd];
+                if (use_d) v += p.beta * D[r + c * p.ldd];
                 C[r + c * p.ldc] = v;
             }
         }
     }
 }
 
-// sums the S split-K partials of one remainder tile in a fixed order (deterministic)
+// sums the S split-K partials of the remainder tiles in a fixed order (deterministic)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const KParams p) {
     const int tile = p.full_tiles + blockIdx.x;
     int tr, tc;
     decode_tile(p, tile, tr, tc);
     const int r0 = tr * BR, c0 = tc * BC;
     const int nr = min(BR, p.M - r0), nc = min(BC, p.N - c0);
-    const bool diag = p.lower_only && (tr == tc);
     const double *ws = p.ws + (long long)blockIdx.x * p.S * TILE_ELEMS;
-    for (int e = threadIdx.x; e < TILE_ELEMS; e += blockDim.x) {
-        int rl = e % BR, cl = e / BR;
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < TILE_ELEMS; e += gridDim.y * blockDim.x) {
+        const int rl = e % BR, cl = e / BR;
         if (rl >= nr || cl >= nc) continue;
-        if (diag && rl < cl) continue;
+        const long long r = r0 + rl, c = c0 + cl;
+        if (p.lower_only && r < c) continue;
         double s = 0.0;
         for (int k = 0; k < p.S; ++k) s += ws[(long long)k * TILE_ELEMS + e];
-        long long r = r0 + rl, c = c0 + cl;
         double v = p.alpha * s;
         if (p.beta != 0.0) v += p.beta * p.D[r + c * p.ldd];
         p.C[r + c * p.ldc] = v;
@@ -295,6 +354,8 @@ int launch_inst(const KParams &p, dim3 grid, cudaStream_t st) {
     if (!attr_set) {
         CVXB_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<XK, YK, VEC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        CVXB_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<XK, YK, VEC>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     dmma_gemm_kernel<XK, YK, VEC><<<grid, THREADS, SMEM_BYTES, st>>>(p);
@@ -304,6 +365,9 @@ int launch_inst(const KParams &p, dim3 grid, cudaStream_t st) {
 }
 
 }  // namespace
+
+size_t dmma_gemm_splitk_ws_doubles() { return (size_t)CTAS_PER_WAVE * TILE_ELEMS; }
+int dmma_gemm_tile_cols() { return BC; }
 
 int dmma_gemm(const GemmDesc &g, cudaStream_t st) {
     if (g.M <= 0 || g.N <= 0) return 0;
@@ -325,7 +389,10 @@ int dmma_gemm(const GemmDesc &g, cudaStream_t st) {
     p.sX = g.sX; p.sY = g.sY; p.sW = g.sW; p.sD = g.sD; p.sC = g.sC;
     long long T = 0;
     if (p.lower_only) {
-        for (int c = p.ct_begin; c < p.ct_end; ++c) T += (p.nTr - c > 0 ? p.nTr - c : 0);
+        for (int c = p.ct_begin; c < p.ct_end; ++c) {
+            int cnt = p.nTr - first_tr(c);
+            T += cnt > 0 ? cnt : 0;
+        }
     } else {
         T = (long long)p.nTr * (p.ct_end - p.ct_begin);
     }
@@ -333,10 +400,10 @@ int dmma_gemm(const GemmDesc &g, cudaStream_t st) {
     // split-K of the remainder wave (deterministic: partials + ordered reduce)
     p.full_tiles = (int)T; p.S = 1; p.kchunk = g.K; p.ws = nullptr;
     if (g.splitk_ws && g.batch == 1 && g.K >= 1024) {
-        int full = (int)(T / kNumSMs) * kNumSMs;
+        int full = (int)(T / CTAS_PER_WAVE) * CTAS_PER_WAVE;
         int rem = (int)T - full;
         if (rem > 0) {
-            int S = kNumSMs / rem;
+            int S = CTAS_PER_WAVE / rem;
             int maxS = g.K / 512;
             if (S > maxS) S = maxS;
             if (S >= 2) {
@@ -356,6 +423,8 @@ int dmma_gemm(const GemmDesc &g, cudaStream_t st) {
     };
     const bool vec = aligned(g.X, g.ldx) && aligned(g.Y, g.ldy) &&
                      (g.batch == 1 || (g.sX % 2 == 0 && g.sY % 2 == 0));
+    p.vec_c = aligned(g.C, g.ldc) && (!g.D || aligned(g.D, g.ldd)) &&
+              (g.batch == 1 || (g.sC % 2 == 0 && g.sD % 2 == 0));
     int rc;
 #define DISPATCH(XK, YK)                                                   \
     rc = vec ? launch_inst<XK, YK, true>(p, grid, st) : launch_inst<XK, YK, false>(p, grid, st)
@@ -366,7 +435,8 @@ int dmma_gemm(const GemmDesc &g, cudaStream_t st) {
 #undef DISPATCH
     if (rc) return rc;
     if (p.S > 1) {
-        splitk_reduce_kernel<<<rem_tiles, 256, 0, st>>>(p);
+        dim3 rg(rem_tiles, 8);
+        splitk_reduce_kernel<<<rg, 256, 0, st>>>(p);
         count_launch();
         CVXB_LAUNCH_CHECK();
     }

@@ -178,7 +178,7 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     const long long ldk = (n + 1) & ~1;
     KCUDA(cudaMalloc(&k->Kmat, (size_t)(ldk > 2 ? ldk : 2) * nn * sizeof(double)));
     const int nblk = (n + NB - 1) / NB + 1;
-    KCUDA(cudaMalloc(&k->inv, (size_t)nblk * NB * NB * sizeof(double)));
+    KCUDA(cudaMalloc(&k->inv, (size_t)2 * nblk * NB * NB * sizeof(double)));   // inv + inv' blocks
     k->nrest = c.mnl + c.sumq + c.sump;
     if (k->nrest > 0) {
         k->ldgs = (k->nrest + 1) & ~1;

@@ -145,7 +145,9 @@ int cvxb_max_step(double *x, const cvxb_dims *dims, double *sigma, double *resul
  * lapack.potrf lapack.c:1471; lapack.potrs lapack.c:1553. */
 int cvxb_syrk_scaled(int n, int k, const double *A, int lda, const double *rowscale,
                      const double *H, int ldh, double *C, int ldc, int device);
-int cvxb_potrf(int n, double *A, int lda, double *work_inv /* n x 128 */, int device);
+/* work_inv: 2 * ceil(n/128) * 128*128 doubles — receives the inverses (and their
+ * transposes) of the 128x128 diagonal blocks of L, consumed by cvxb_potrs */
+int cvxb_potrf(int n, double *A, int lda, double *work_inv, int device);
 int cvxb_potrs(int n, const double *L, int ldl, const double *inv, double *b, int device);
 /* plain C = alpha * op(A) op(B) + beta*C on the DMMA kernel (tests / 's' congruence) */
 int cvxb_gemm(int transa, int transb, int m, int n, int k, double alpha, const double *A,

@@ -131,11 +131,11 @@ def test_building_blocks_gemm_potrf():
         assert rc == 0, _lib.last_error()
         ref = 0.7 * (A.T if ta == "T" else A) @ (B.T if tb == "T" else B) - 0.3 * Cm
         assert relerr(dC.cpu().numpy().T, ref) < 1e-13
-    for n in (1, 100, 128, 129, 700):
+    for n in (1, 100, 128, 129, 700, 1333):
         B = rng.standard_normal((n, n))
         S = B @ B.T + n * np.eye(n)
         dS = torch.from_numpy(S.copy()).cuda()                         # symmetric: layout-agnostic
-        inv = torch.zeros(((n + 127) // 128 + 1) * 128 * 128, dtype=torch.float64, device="cuda")
+        inv = torch.zeros(2 * ((n + 127) // 128) * 128 * 128, dtype=torch.float64, device="cuda")
         rc = lib.cvxb_potrf(n, dS.data_ptr(), n, inv.data_ptr(), 0)
         assert rc == 0, _lib.last_error()
         L = np.tril(dS.cpu().numpy().T)
