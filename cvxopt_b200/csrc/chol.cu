@@ -94,7 +94,7 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
                     if (!bad && tid == 0) atomicCAS(info, 0, joff + c0 + j + 1);
                     bad = true;
                 }
-                const double s = sqrt(piv), rs = 1.0 / s;
+                const double rs = rsqrt(piv), s = piv * rs;      // one long-latency op per pivot
                 if (lane == j) rdiag = rs;
                 double lij = __shfl_sync(0xffffffffu, colv, i + 8 * gj) * rs;
                 const double lk0 = __shfl_sync(0xffffffffu, colv, 2 * g + 8 * gj) * rs;
@@ -199,45 +199,59 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
     for (int s = PB; s < NB; s <<= 1) {
         const int sb = s / PB;                   // 8-blocks per side
         const int tp = sb * sb;                  // tiles per pair
-        const int npairs = NB / (2 * s);
-        // T = L21 * X11  -> stored in the (unused) upper block of the pair
-        for (int idx = warp; idx < npairs * tp; idx += 8) {
-            const int pr = idx / tp, loc = idx - pr * tp;
-            const int ti = loc % sb, tj = loc / sb;
-            const int o = pr * 2 * s;
-            double c0v = 0.0, c1v = 0.0;
-            for (int kb = tj; kb < sb; ++kb) {
+        const int ntiles = (NB / (2 * s)) * tp;
+        // phase 0: T = L21 * X11 -> stored in the (unused) upper block of the pair
+        // phase 1: X21 = - X22 * T
+        // each warp walks its tiles four at a time so four DMMA chains are in flight
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+            for (int base = warp * 4; base < ntiles; base += 32) {
+                double c[4][2];
+                int oo[4], ti[4], tj[4];
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const int k = o + kb * 8 + kk * 4 + t4;
-                    const double af = M[(o + s + ti * 8 + g4) + k * LDM];
-                    const double bf = M[k + (o + tj * 8 + g4) * LDM];
-                    dmma(c0v, c1v, af, bf);
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = min(base + u, ntiles - 1);
+                    const int pr = idx / tp, loc = idx - pr * tp;
+                    ti[u] = loc % sb; tj[u] = loc / sb; oo[u] = pr * 2 * s;
+                    c[u][0] = c[u][1] = 0.0;
+                }
+                for (int kb = 0; kb < sb; ++kb) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        // X11 / X22 are lower triangular: skip the zero k blocks
+                        const bool live = phase == 0 ? (kb >= tj[u]) : (kb <= ti[u]);
+                        if (!live) continue;
+                        const int o = oo[u];
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const int k = kb * 8 + kk * 4 + t4;
+                            double af, bf;
+                            if (phase == 0) {
+                                af = M[(o + s + ti[u] * 8 + g4) + (o + k) * LDM];
+                                bf = M[(o + k) + (o + tj[u] * 8 + g4) * LDM];
+                            } else {
+                                af = M[(o + s + ti[u] * 8 + g4) + (o + s + k) * LDM];
+                                bf = M[(o + k) + (o + s + tj[u] * 8 + g4) * LDM];
+                            }
+                            dmma(c[u][0], c[u][1], af, bf);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (base + u >= ntiles) continue;
+                    const int o = oo[u];
+                    if (phase == 0) {
+                        M[(o + ti[u] * 8 + g4) + (o + s + tj[u] * 8 + t4 * 2) * LDM] = c[u][0];
+                        M[(o + ti[u] * 8 + g4) + (o + s + tj[u] * 8 + t4 * 2 + 1) * LDM] = c[u][1];
+                    } else {
+                        M[(o + s + ti[u] * 8 + g4) + (o + tj[u] * 8 + t4 * 2) * LDM] = -c[u][0];
+                        M[(o + s + ti[u] * 8 + g4) + (o + tj[u] * 8 + t4 * 2 + 1) * LDM] = -c[u][1];
+                    }
                 }
             }
-            M[(o + ti * 8 + g4) + (o + s + tj * 8 + t4 * 2) * LDM] = c0v;
-            M[(o + ti * 8 + g4) + (o + s + tj * 8 + t4 * 2 + 1) * LDM] = c1v;
+            __syncthreads();
         }
-        __syncthreads();
-        // X21 = - X22 * T
-        for (int idx = warp; idx < npairs * tp; idx += 8) {
-            const int pr = idx / tp, loc = idx - pr * tp;
-            const int ti = loc % sb, tj = loc / sb;
-            const int o = pr * 2 * s;
-            double c0v = 0.0, c1v = 0.0;
-            for (int kb = 0; kb <= ti; ++kb) {
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const int k = kb * 8 + kk * 4 + t4;
-                    const double af = M[(o + s + ti * 8 + g4) + (o + s + k) * LDM];
-                    const double bf = M[(o + k) + (o + s + tj * 8 + g4) * LDM];
-                    dmma(c0v, c1v, af, bf);
-                }
-            }
-            M[(o + s + ti * 8 + g4) + (o + tj * 8 + t4 * 2) * LDM] = -c0v;
-            M[(o + s + ti * 8 + g4) + (o + tj * 8 + t4 * 2 + 1) * LDM] = -c1v;
-        }
-        __syncthreads();
     }
     for (int e = tid; e < NB * NB; e += 256) {
         int i = e & (NB - 1), k = e >> 7;

@@ -225,7 +225,8 @@ __global__ void symmetrize_kernel(double *A, long long lda, int n, long long str
     }
 }
 
-// ---- GEMV-T: one warp per column
+// ---- GEMV-T: one warp per column; 16-byte loads, 8 in flight per lane
+template <bool VEC, bool HAS_W>
 __global__ void __launch_bounds__(256)
 gemv_t_kernel(int nrows, int ncols, const double *__restrict__ A, long long lda,
               const double *__restrict__ w, const double *__restrict__ x, double alpha,
@@ -235,24 +236,36 @@ gemv_t_kernel(int nrows, int ncols, const double *__restrict__ A, long long lda,
     if (c >= ncols) return;
     const double *a = A + c * lda;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int k = lane;
-    if (w) {
-        for (; k + 96 < nrows; k += 128) {
-            s0 += a[k] * (w[k] * x[k]);
-            s1 += a[k + 32] * (w[k + 32] * x[k + 32]);
-            s2 += a[k + 64] * (w[k + 64] * x[k + 64]);
-            s3 += a[k + 96] * (w[k + 96] * x[k + 96]);
+    int k = 0;
+    if (VEC) {
+        const double2 *a2 = reinterpret_cast<const double2 *>(a);
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        const double2 *w2 = reinterpret_cast<const double2 *>(w);
+        const int n2 = nrows >> 1;
+        int k2 = lane;
+        for (; k2 + 96 < n2; k2 += 128) {
+            double2 v0 = a2[k2], v1 = a2[k2 + 32], v2 = a2[k2 + 64], v3 = a2[k2 + 96];
+            double2 u0 = x2[k2], u1 = x2[k2 + 32], u2 = x2[k2 + 64], u3 = x2[k2 + 96];
+            if (HAS_W) {
+                double2 q0 = w2[k2], q1 = w2[k2 + 32], q2 = w2[k2 + 64], q3 = w2[k2 + 96];
+                u0.x *= q0.x; u0.y *= q0.y; u1.x *= q1.x; u1.y *= q1.y;
+                u2.x *= q2.x; u2.y *= q2.y; u3.x *= q3.x; u3.y *= q3.y;
+            }
+            s0 += v0.x * u0.x; s0 += v0.y * u0.y;
+            s1 += v1.x * u1.x; s1 += v1.y * u1.y;
+            s2 += v2.x * u2.x; s2 += v2.y * u2.y;
+            s3 += v3.x * u3.x; s3 += v3.y * u3.y;
         }
-        for (; k < nrows; k += 32) s0 += a[k] * (w[k] * x[k]);
+        for (; k2 < n2; k2 += 32) {
+            double2 v0 = a2[k2], u0 = x2[k2];
+            if (HAS_W) { double2 q0 = w2[k2]; u0.x *= q0.x; u0.y *= q0.y; }
+            s0 += v0.x * u0.x; s0 += v0.y * u0.y;
+        }
+        k = n2 * 2 + lane;            // odd tail row (at most one)
     } else {
-        for (; k + 96 < nrows; k += 128) {
-            s0 += a[k] * x[k];
-            s1 += a[k + 32] * x[k + 32];
-            s2 += a[k + 64] * x[k + 64];
-            s3 += a[k + 96] * x[k + 96];
-        }
-        for (; k < nrows; k += 32) s0 += a[k] * x[k];
+        k = lane;
     }
+    for (; k < nrows; k += 32) s1 += a[k] * (HAS_W ? w[k] * x[k] : x[k]);
     double s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) y[c] = (beta == 0.0) ? alpha * s : alpha * s + beta * y[c];
 }
@@ -389,7 +402,16 @@ int scale_s(const ConeLayout &c, const DevScaling &W, const double *src, long lo
 int gemv_t(int nrows, int ncols, const double *A, long long lda, const double *w, const double *x,
            double alpha, double beta, double *y, cudaStream_t st) {
     if (ncols <= 0) return 0;
-    gemv_t_kernel<<<(ncols + 7) / 8, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
+    const bool vec = ((uintptr_t)A % 16 == 0) && (lda % 2 == 0) && ((uintptr_t)x % 16 == 0) &&
+                     (!w || (uintptr_t)w % 16 == 0);
+    const int grid = (ncols + 7) / 8;
+    if (vec) {
+        if (w) gemv_t_kernel<true, true><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
+        else   gemv_t_kernel<true, false><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
+    } else {
+        if (w) gemv_t_kernel<false, true><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
+        else   gemv_t_kernel<false, false><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
+    }
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;
