@@ -145,3 +145,48 @@ def test_building_blocks_gemm_potrf():
         rc = lib.cvxb_potrs(n, dS.data_ptr(), n, inv.data_ptr(), db.data_ptr(), 0)
         assert rc == 0
         assert relerr(db.cpu().numpy(), np.linalg.solve(S, b)) < 1e-11
+
+
+@pytest.mark.parametrize("dims", [{"l": 5, "q": [4, 9], "s": [3, 7]}, {"l": 0, "q": [], "s": [20]}, {"l": 11, "q": [], "s": []}])
+def test_misc_solvers_mirror(dims):
+    """cvxopt_b200.misc_solvers.{scale,pack,unpack,pack2,symm} vs the oracle restatement."""
+    from cvxopt_b200 import misc_solvers as ms
+    W, _ = random_scaling(dims, seed=4)
+    rng = np.random.Generator(np.random.PCG64(5))
+    K = cone_dim(dims)
+    _, _, _, _, cp = ko.cone_sizes(dims)
+    il = []
+    off = dims["l"] + sum(dims["q"])
+    mask = np.ones(K, bool)            # strict upper triangles of 's' blocks are not significant
+    for k in dims["s"]:
+        M = np.ones((k, k), bool)
+        M[np.triu_indices(k, 1)] = False
+        mask[off:off + k * k] = M.reshape(-1, order="F")
+        off += k * k
+    for trans in "NT":
+        for inverse in "NI":
+            x = np.asfortranarray(rng.standard_normal((K, 5)))
+            xo = x.copy()
+            ms.scale(x, W, trans, inverse)
+            ko.scale(xo, W, trans, inverse)
+            assert relerr(x[mask], xo[mask]) < 1e-12, (trans, inverse)
+    x = rng.standard_normal(K)
+    y, yo = np.zeros(cp), np.zeros(cp)
+    ms.pack(x, y, dims)
+    ko.pack(x, yo, dims)
+    assert np.array_equal(y, yo)
+    z, zo = rng.standard_normal(K), None
+    zo = z.copy()
+    ms.unpack(y, z, dims)
+    ko.unpack(yo, zo, dims)
+    assert np.array_equal(z, zo)
+    X = np.asfortranarray(rng.standard_normal((K, 3)))
+    Xo = X.copy()
+    ms.pack2(X, dims)
+    ko.pack2(Xo, dims)
+    assert np.array_equal(X[:cp], Xo[:cp])
+    S = rng.standard_normal(49)
+    So = S.copy()
+    ms.symm(S, 7)
+    ko.symm(So, 7)
+    assert np.array_equal(S, So)
