@@ -5,8 +5,10 @@ the host-side mirror of the reference's kktsolver / misc_solvers interface.
 """
 from ._lib import load, exported_symbols, LIB_PATH  # noqa: F401
 from .kkt import kkt_chol, KKTChol  # noqa: F401
+from .batch import QPBatch, qp_batch, qp_batch_distributed, shard_bounds  # noqa: F401
 
-__all__ = ["kkt_chol", "KKTChol", "load", "device_count", "launch_count"]
+__all__ = ["kkt_chol", "KKTChol", "QPBatch", "qp_batch", "qp_batch_distributed", "load",
+           "device_count", "launch_count"]
 
 
 def device_count():

@@ -78,6 +78,7 @@ _SIGS = {
     "cvxb_batch_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int]),
     "cvxb_batch_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "cvxb_batch_stats": (C.c_int, [C.c_void_p, c_double_p, c_int_p]),
     "cvxb_batch_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
 }

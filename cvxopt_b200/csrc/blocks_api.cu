@@ -241,10 +241,4 @@ int cvxb_triusc(double *, const cvxb_dims *, int) { CVXB_NOT_YET("triusc"); }
 int cvxb_sdot(const double *, const double *, const cvxb_dims *, double *, int) { CVXB_NOT_YET("sdot"); }
 int cvxb_max_step(double *, const cvxb_dims *, double *, double *, int) { CVXB_NOT_YET("max_step"); }
 
-int cvxb_batch_create(cvxb_batch **, int, int, int, int) { CVXB_NOT_YET("batch_create"); }
-void cvxb_batch_destroy(cvxb_batch *) {}
-int cvxb_batch_load(cvxb_batch *, const double *, const double *, const double *, const double *, int) { CVXB_NOT_YET("batch_load"); }
-int cvxb_batch_solve(cvxb_batch *, int, double, double, double) { CVXB_NOT_YET("batch_solve"); }
-int cvxb_batch_results(cvxb_batch *, double *, double *, double *, int *, int *, double *, double *, int) { CVXB_NOT_YET("batch_results"); }
-
 }  // extern "C"

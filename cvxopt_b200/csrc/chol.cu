@@ -38,8 +38,11 @@ constexpr int POTF2_SMEM = (NB * LDM + NB * SP + 4 * 80) * 8;
 // their fragments with two DMMA k-steps per tile.  The inverse is then built in shared
 // memory by recursive doubling (X21 = -X22 (L21 X11)) with DMMA tile products.
 __global__ void __launch_bounds__(256, 1)
-potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, int *info, int joff) {
+potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, int *info, int joff,
+                 long long sA, long long sInv) {
     extern __shared__ __align__(16) double sm[];
+    A += (long long)blockIdx.x * sA; inv += (long long)blockIdx.x * sInv;
+    invT += (long long)blockIdx.x * sInv; info += blockIdx.x;
     double *M = sm;                    // NB x LDM, column-major
     double *P = M + NB * LDM;          // NB x SP, row-major panel
     double *Dw = P + NB * SP;          // 4 private copies of the 8x8 factor (+ reciprocal diagonal)
@@ -276,8 +279,14 @@ constexpr int TRSV_SMEM = (TR_R * NB * TR_CH + 4 * NB) * 8;
 template <bool TRANS, bool VEC>
 __global__ void __launch_bounds__(256, 1)
 trsv_kernel(int n, const double *__restrict__ L, long long ldl, const double *__restrict__ inv,
-            const double *__restrict__ invT, double *b, int *flags, int epoch) {
+            const double *__restrict__ invT, double *b, int *flags, int epoch, long long sL,
+            long long sInv, long long sb) {
     extern __shared__ __align__(16) double sm[];
+    {   // batched: blockIdx.y selects the problem (blocks of one problem keep ascending order)
+        const long long pb = blockIdx.y;
+        L += pb * sL; inv += pb * sInv; invT += pb * sInv; b += pb * sb;
+        flags += pb * ((n + NB - 1) / NB);
+    }
     double *ring = sm;                          // TR_R x (32 cols x 128 rows), column-contiguous
     double *xs = ring + TR_R * NB * TR_CH;      // 128
     double *part = xs + NB;                     // 2 x 128
@@ -415,6 +424,7 @@ int chol_work_create(CholWork &w) {
     CVXB_CUDA(cudaEventCreateWithFlags(&w.ev_end_u, cudaEventDisableTiming));
     CVXB_CUDA(cudaMalloc(&w.d_info, sizeof(int)));
     CVXB_CUDA(cudaMemset(w.d_info, 0, sizeof(int)));
+    w.flags_cap = 4096;
     CVXB_CUDA(cudaMalloc(&w.d_flags, 4096 * sizeof(int)));
     CVXB_CUDA(cudaMemset(w.d_flags, 0, 4096 * sizeof(int)));
     CVXB_CUDA(cudaMalloc(&w.splitk_ws, dmma_gemm_splitk_ws_doubles() * sizeof(double)));
@@ -470,7 +480,7 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
         double *Ajj = A + j + (long long)j * lda;
         double *invj = inv + (long long)jb * NB * NB;
         double *invTj = inv + (long long)(nblk + jb) * NB * NB;
-        potf2_inv_kernel<<<1, 256, POTF2_SMEM, P>>>(Ajj, lda, wj, invj, invTj, w.d_info, j);
+        potf2_inv_kernel<<<1, 256, POTF2_SMEM, P>>>(Ajj, lda, wj, invj, invTj, w.d_info, j, 0, 0);
         count_launch();
         CVXB_LAUNCH_CHECK();
         if (m <= 0) break;
@@ -516,32 +526,84 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
 }
 
 int trsv_lower(int n, const double *L, int ldl, const double *inv, double *b, bool trans,
-               CholWork &w, cudaStream_t st) {
-    if (n <= 0) return 0;
+               CholWork &w, cudaStream_t st, int batch, long long sL, long long sInv, long long sb) {
+    if (n <= 0 || batch <= 0) return 0;
     const int nblk = (n + NB - 1) / NB;
-    if (nblk > 4096) {
-        set_error("trsv_lower: n too large");
-        return CVXB_E_ARG;
+    if ((long long)nblk * batch > w.flags_cap) {
+        if (w.d_flags) CVXB_CUDA(cudaFree(w.d_flags));
+        w.flags_cap = (long long)nblk * batch;
+        CVXB_CUDA(cudaMalloc(&w.d_flags, (size_t)w.flags_cap * sizeof(int)));
+        CVXB_CUDA(cudaMemset(w.d_flags, 0, (size_t)w.flags_cap * sizeof(int)));
     }
     const int epoch = ++g_trsv_epoch;
     const double *invT = inv + (long long)nblk * NB * NB;
-    const bool vec = ((uintptr_t)L % 16 == 0) && (ldl % 2 == 0);
-    if (trans) {
-        if (vec) trsv_kernel<true, true><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
-        else     trsv_kernel<true, false><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
-    } else {
-        if (vec) trsv_kernel<false, true><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
-        else     trsv_kernel<false, false><<<nblk, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch);
-    }
+    const bool vec = ((uintptr_t)L % 16 == 0) && (ldl % 2 == 0) && (batch == 1 || sL % 2 == 0);
+    dim3 grid(nblk, batch);
+#define TRSV_LAUNCH(T, V) trsv_kernel<T, V><<<grid, 256, TRSV_SMEM, st>>>(n, L, ldl, inv, invT, b, w.d_flags, epoch, sL, sInv, sb)
+    if (trans) { if (vec) TRSV_LAUNCH(true, true); else TRSV_LAUNCH(true, false); }
+    else       { if (vec) TRSV_LAUNCH(false, true); else TRSV_LAUNCH(false, false); }
+#undef TRSV_LAUNCH
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;
 }
 
 int potrs_lower(int n, const double *L, int ldl, const double *inv, double *b, CholWork &w,
-                cudaStream_t st) {
-    CVXB_TRY(trsv_lower(n, L, ldl, inv, b, false, w, st));
-    CVXB_TRY(trsv_lower(n, L, ldl, inv, b, true, w, st));
+                cudaStream_t st, int batch, long long sL, long long sInv, long long sb) {
+    CVXB_TRY(trsv_lower(n, L, ldl, inv, b, false, w, st, batch, sL, sInv, sb));
+    CVXB_TRY(trsv_lower(n, L, ldl, inv, b, true, w, st, batch, sL, sInv, sb));
+    return 0;
+}
+
+namespace {
+__global__ void copy2d_batched_kernel(const double *src, long long lds, long long ssrc, double *dst,
+                                      long long ldd, long long sdst, int rows, int cols) {
+    const long long pb = blockIdx.z;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r < rows && c < cols) dst[pb * sdst + r + (long long)c * ldd] = src[pb * ssrc + r + (long long)c * lds];
+}
+}  // namespace
+
+// Batched Cholesky of `batch` independent n x n matrices (stride sA, inverse blocks stride
+// sInv).  The batch itself fills the machine, so the steps run back to back on one stream
+// (no look-ahead).  d_info: one int per problem.  panel: batch * ldw * NB doubles.
+int potrf_lower_batched(int n, double *A, int lda, long long sA, double *inv, long long sInv,
+                        int batch, int *d_info, double *panel, int ldw, cudaStream_t st) {
+    if (n <= 0 || batch <= 0) return 0;
+    const int nblk = (n + NB - 1) / NB;
+    CVXB_CUDA(cudaMemsetAsync(d_info, 0, (size_t)batch * sizeof(int), st));
+    const long long sW = (long long)ldw * NB;
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int j = jb * NB;
+        const int wj = (n - j < NB) ? (n - j) : NB;
+        const int m = n - j - wj;
+        double *Ajj = A + j + (long long)j * lda;
+        double *invj = inv + (long long)jb * NB * NB;
+        double *invTj = inv + (long long)(nblk + jb) * NB * NB;
+        potf2_inv_kernel<<<batch, 256, POTF2_SMEM, st>>>(Ajj, lda, wj, invj, invTj, d_info, j, sA, sInv);
+        count_launch();
+        CVXB_LAUNCH_CHECK();
+        if (m <= 0) break;
+        double *A21 = Ajj + wj;
+        double *A22 = A21 + (long long)wj * lda;
+        GemmDesc g;
+        g.M = m; g.N = wj; g.K = wj;
+        g.X = A21; g.ldx = lda; g.x_kmajor = false; g.sX = sA;
+        g.Y = invj; g.ldy = NB; g.y_kmajor = false; g.sY = sInv;
+        g.C = panel; g.ldc = ldw; g.sC = sW; g.batch = batch;
+        CVXB_TRY(dmma_gemm(g, st));
+        GemmDesc u;
+        u.M = m; u.N = m; u.K = wj;
+        u.X = panel; u.ldx = ldw; u.x_kmajor = false; u.sX = sW;
+        u.Y = panel; u.ldy = ldw; u.y_kmajor = false; u.sY = sW;
+        u.D = A22; u.ldd = lda; u.sD = sA; u.C = A22; u.ldc = lda; u.sC = sA;
+        u.alpha = -1.0; u.beta = 1.0; u.lower_only = true; u.batch = batch;
+        CVXB_TRY(dmma_gemm(u, st));
+        dim3 cg((m + 255) / 256, wj, batch);
+        copy2d_batched_kernel<<<cg, 256, 0, st>>>(panel, ldw, sW, A21, lda, sA, m, wj);
+        count_launch();
+        CVXB_LAUNCH_CHECK();
+    }
     return 0;
 }
 

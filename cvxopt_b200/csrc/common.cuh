@@ -119,7 +119,8 @@ struct CholWork {
     cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr, ev_end_p = nullptr,
                 ev_end_u = nullptr;
     int *d_info = nullptr;                // device flag
-    int *d_flags = nullptr;               // trsv progress flags (>= n/NB + 1 ints)
+    int *d_flags = nullptr;               // trsv progress flags (batch * ceil(n/NB) ints)
+    long long flags_cap = 0;
     double *splitk_ws = nullptr;
     double *panel[2] = {nullptr, nullptr};   // out-of-place TRSM results (double-buffered)
     int panel_rows = 0;
@@ -128,9 +129,14 @@ int chol_work_create(CholWork &w);
 void chol_work_destroy(CholWork &w);
 int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_t st);
 // b := L^{-T} L^{-1} b  (potrs with one right-hand side)
+// batched variants: problem p uses L + p*sL, inv + p*sInv, b + p*sb
 int potrs_lower(int n, const double *L, int ldl, const double *inv, double *b, CholWork &w,
-                cudaStream_t st);
+                cudaStream_t st, int batch = 1, long long sL = 0, long long sInv = 0,
+                long long sb = 0);
 int trsv_lower(int n, const double *L, int ldl, const double *inv, double *b, bool trans,
-               CholWork &w, cudaStream_t st);
+               CholWork &w, cudaStream_t st, int batch = 1, long long sL = 0, long long sInv = 0,
+               long long sb = 0);
+int potrf_lower_batched(int n, double *A, int lda, long long sA, double *inv, long long sInv,
+                        int batch, int *d_info, double *panel, int ldw, cudaStream_t st);
 
 }  // namespace cvxb

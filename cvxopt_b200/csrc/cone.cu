@@ -230,10 +230,13 @@ template <bool VEC, bool HAS_W>
 __global__ void __launch_bounds__(256)
 gemv_t_kernel(int nrows, int ncols, const double *__restrict__ A, long long lda,
               const double *__restrict__ w, const double *__restrict__ x, double alpha,
-              double beta, double *y) {
+              double beta, double *y, GemvBatch bs) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long c = (long long)blockIdx.x * 8 + warp;
     if (c >= ncols) return;
+    const long long pb = blockIdx.y;
+    A += pb * bs.sA; x += pb * bs.sx; y += pb * bs.sy;
+    if (HAS_W) w += pb * bs.sw;
     const double *a = A + c * lda;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     int k = 0;
@@ -273,8 +276,10 @@ gemv_t_kernel(int nrows, int ncols, const double *__restrict__ A, long long lda,
 constexpr int GN_CH = 128;   // columns per chunk
 __global__ void __launch_bounds__(256)
 gemv_n_partial_kernel(int nrows, int ncols, const double *__restrict__ A, long long lda,
-                      const double *__restrict__ x, double *ws) {
+                      const double *__restrict__ x, double *ws, GemvBatch bs, long long sws) {
     __shared__ double xs[GN_CH];
+    A += (long long)blockIdx.z * bs.sA; x += (long long)blockIdx.z * bs.sx;
+    ws += (long long)blockIdx.z * sws;
     const int c0 = blockIdx.y * GN_CH;
     const int nc = min(GN_CH, ncols - c0);
     if (threadIdx.x < GN_CH) xs[threadIdx.x] = (threadIdx.x < nc) ? x[c0 + threadIdx.x] : 0.0;
@@ -294,9 +299,12 @@ gemv_n_partial_kernel(int nrows, int ncols, const double *__restrict__ A, long l
     ws[(long long)blockIdx.y * nrows + k] = (s0 + s1) + (s2 + s3);
 }
 __global__ void gemv_n_reduce_kernel(int nrows, int nchunks, const double *ws, const double *w,
-                                     double alpha, double beta, double *y) {
+                                     double alpha, double beta, double *y, GemvBatch bs,
+                                     long long sws) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nrows) return;
+    ws += (long long)blockIdx.y * sws; y += (long long)blockIdx.y * bs.sy;
+    if (w) w += (long long)blockIdx.y * bs.sw;
     double s = 0.0;
     for (int ch = 0; ch < nchunks; ++ch) s += ws[(long long)ch * nrows + k];
     if (w) s *= w[k];
@@ -400,17 +408,18 @@ int scale_s(const ConeLayout &c, const DevScaling &W, const double *src, long lo
 }
 
 int gemv_t(int nrows, int ncols, const double *A, long long lda, const double *w, const double *x,
-           double alpha, double beta, double *y, cudaStream_t st) {
-    if (ncols <= 0) return 0;
+           double alpha, double beta, double *y, cudaStream_t st, const GemvBatch &bs) {
+    if (ncols <= 0 || bs.batch <= 0) return 0;
     const bool vec = ((uintptr_t)A % 16 == 0) && (lda % 2 == 0) && ((uintptr_t)x % 16 == 0) &&
-                     (!w || (uintptr_t)w % 16 == 0);
-    const int grid = (ncols + 7) / 8;
+                     (!w || (uintptr_t)w % 16 == 0) &&
+                     (bs.batch == 1 || (bs.sA % 2 == 0 && bs.sx % 2 == 0 && bs.sw % 2 == 0));
+    dim3 grid((ncols + 7) / 8, bs.batch);
     if (vec) {
-        if (w) gemv_t_kernel<true, true><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
-        else   gemv_t_kernel<true, false><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
+        if (w) gemv_t_kernel<true, true><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y, bs);
+        else   gemv_t_kernel<true, false><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y, bs);
     } else {
-        if (w) gemv_t_kernel<false, true><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
-        else   gemv_t_kernel<false, false><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y);
+        if (w) gemv_t_kernel<false, true><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y, bs);
+        else   gemv_t_kernel<false, false><<<grid, 256, 0, st>>>(nrows, ncols, A, lda, w, x, alpha, beta, y, bs);
     }
     count_launch();
     CVXB_LAUNCH_CHECK();
@@ -420,17 +429,18 @@ int gemv_t(int nrows, int ncols, const double *A, long long lda, const double *w
 int gemv_n_chunks(int ncols) { return ncols <= 0 ? 1 : (ncols + GN_CH - 1) / GN_CH; }
 
 int gemv_n(int nrows, int ncols, const double *A, long long lda, const double *w, const double *x,
-           double alpha, double beta, double *y, double *ws, cudaStream_t st) {
-    if (nrows <= 0) return 0;
+           double alpha, double beta, double *y, double *ws, cudaStream_t st, const GemvBatch &bs) {
+    if (nrows <= 0 || bs.batch <= 0) return 0;
     const int nch = gemv_n_chunks(ncols);
+    const long long sws = (long long)nch * nrows;        // workspace per problem
     if (ncols > 0) {
-        dim3 grid((nrows + 255) / 256, nch);
-        gemv_n_partial_kernel<<<grid, 256, 0, st>>>(nrows, ncols, A, lda, x, ws);
+        dim3 grid((nrows + 255) / 256, nch, bs.batch);
+        gemv_n_partial_kernel<<<grid, 256, 0, st>>>(nrows, ncols, A, lda, x, ws, bs, sws);
         count_launch();
         CVXB_LAUNCH_CHECK();
     }
-    gemv_n_reduce_kernel<<<(nrows + 255) / 256, 256, 0, st>>>(nrows, ncols > 0 ? nch : 0, ws, w,
-                                                              alpha, beta, y);
+    dim3 rg((nrows + 255) / 256, bs.batch);
+    gemv_n_reduce_kernel<<<rg, 256, 0, st>>>(nrows, ncols > 0 ? nch : 0, ws, w, alpha, beta, y, bs, sws);
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;

@@ -59,17 +59,21 @@ int unpack_s(const ConeLayout &c, const double *src, long long lds, double *dst,
              int xc, cudaStream_t st);
 
 // ---- GEMV (HBM-bound) -------------------------------------------------------------
+// optional batching: problem b uses A + b*sA, w + b*sw, x + b*sx, y + b*sy
+struct GemvBatch {
+    int batch = 1;
+    long long sA = 0, sw = 0, sx = 0, sy = 0;
+};
 // y[c] = alpha * sum_k A[k + c*lda] * (w ? w[k] : 1) * x[k] + beta * y[c],  c < ncols, k < nrows
 int gemv_t(int nrows, int ncols, const double *A, long long lda, const double *w, const double *x,
-           double alpha, double beta, double *y, cudaStream_t st);
+           double alpha, double beta, double *y, cudaStream_t st,
+           const GemvBatch &bs = GemvBatch());
 // y[k] = alpha * (w ? w[k] : 1) * sum_c A[k + c*lda] x[c] + beta * y[k]
-// ws: >= nrows * gemv_n_chunks(ncols) doubles
+// ws: >= batch * nrows * gemv_n_chunks(ncols) doubles
 int gemv_n_chunks(int ncols);
 int gemv_n(int nrows, int ncols, const double *A, long long lda, const double *w, const double *x,
-           double alpha, double beta, double *y, double *ws, cudaStream_t st);
-// y = alpha * H x + beta * y with H symmetric, lower triangle stored (n x n)
-int symv_lower(int n, const double *H, long long ldh, const double *x, double alpha, double beta,
-               double *y, double *ws, cudaStream_t st);
+           double alpha, double beta, double *y, double *ws, cudaStream_t st,
+           const GemvBatch &bs = GemvBatch());
 // small elementwise helpers
 int vec_mul(int n, const double *a, const double *b, double *out, cudaStream_t st);  // out = a.*b
 int vec_axpby(int n, double alpha, const double *x, double beta, double *y, cudaStream_t st);

@@ -158,11 +158,16 @@ int cvxb_gemm(int transa, int transb, int m, int n, int k, double alpha, const d
  * over solvers.qp).  Problems are  min 1/2 x'P x + q'x  s.t.  G x <= h. */
 int cvxb_batch_create(cvxb_batch **out, int nprob, int n, int m, int device);
 void cvxb_batch_destroy(cvxb_batch *b);
+/* P: nprob x (n x n, ld n); q: nprob x n; G: nprob x (m x n column-major, ld m); h: nprob x m */
 int cvxb_batch_load(cvxb_batch *b, const double *P, const double *q, const double *G,
                     const double *h, int space);
 int cvxb_batch_solve(cvxb_batch *b, int maxiters, double abstol, double reltol, double feastol);
+/* status: 1 optimal, 2 maximum iterations reached, 3 singular KKT matrix ('unknown' in the
+ * reference for 2 and 3).  x/s/z may be device pointers (space), scalars go to host memory. */
 int cvxb_batch_results(cvxb_batch *b, double *x, double *s, double *z, int *status,
                        int *iters, double *pobj, double *dobj, int space);
+/* CUDA-event time of the last cvxb_batch_solve and the number of lock-step iterations run */
+int cvxb_batch_stats(cvxb_batch *b, double *solve_ms, int *iterations);
 
 #ifdef __cplusplus
 }

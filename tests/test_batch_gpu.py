@@ -1,0 +1,66 @@
+"""Batch / device-resident IPM (BASELINE config 4) vs the reference: a Python loop over
+solvers.qp (oracle/_ref) on the same problems — same status, same iteration count per problem,
+objectives to rtol 1e-8, x to 1e-6."""
+import numpy as np
+import pytest
+
+from problems import dense_qp
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(B, n, m, seed0=0):
+    Ps, qs, Gs, hs = [], [], [], []
+    for k in range(B):
+        P, q, G, h = dense_qp(n, m, seed=seed0 + k)
+        Ps.append(P); qs.append(q); Gs.append(G); hs.append(h)
+    return np.stack(Ps), np.stack(qs), np.stack(Gs), np.stack(hs)
+
+
+def ref_loop(ref, P, q, G, h):
+    from cvxopt import matrix, solvers
+    out = []
+    for k in range(P.shape[0]):
+        out.append(solvers.qp(matrix(P[k]), matrix(q[k]), matrix(G[k]), matrix(h[k]), kktsolver="chol"))
+    return out
+
+
+@pytest.mark.parametrize("B,n,m", [(5, 30, 70), (3, 150, 321), (2, 257, 300), (1, 300, 640)])
+def test_batch_matches_reference_loop(ref, B, n, m):
+    import cvxopt_b200
+    P, q, G, h = make_batch(B, n, m, seed0=10 * B)
+    got = cvxopt_b200.qp_batch(P, q, G, h)
+    want = ref_loop(ref, P, q, G, h)
+    for k in range(B):
+        assert got["status"][k] == want[k]["status"] == "optimal"
+        assert got["iterations"][k] == want[k]["iterations"], (k, got["iterations"], want[k]["iterations"])
+        np.testing.assert_allclose(got["primal objective"][k], want[k]["primal objective"], rtol=1e-8)
+        np.testing.assert_allclose(got["dual objective"][k], want[k]["dual objective"], rtol=1e-8)
+        np.testing.assert_allclose(got["x"][k], np.array(want[k]["x"]).ravel(), rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(got["s"][k], np.array(want[k]["s"]).ravel(), rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(got["z"][k], np.array(want[k]["z"]).ravel(), rtol=1e-5, atol=1e-7)
+
+
+def test_batch_mixed_difficulty_masks():
+    """problems converge at different iterations: early finishers must stay frozen"""
+    import cvxopt_b200
+    P, q, G, h = make_batch(4, 40, 90, seed0=3)
+    h[1] *= 50.0          # different scaling -> different iteration counts
+    q[2] *= 1e-3
+    got = cvxopt_b200.qp_batch(P, q, G, h)
+    assert all(s == "optimal" for s in got["status"])
+    for k in range(4):
+        single = cvxopt_b200.qp_batch(P[k:k + 1], q[k:k + 1], G[k:k + 1], h[k:k + 1])
+        assert single["iterations"][0] == got["iterations"][k]
+        np.testing.assert_allclose(single["x"][0], got["x"][k], rtol=1e-9, atol=1e-12)
+
+
+def test_batch_rank_deficient_raises():
+    import cvxopt_b200
+    n, m = 20, 5
+    P = np.zeros((1, n, n))
+    q = np.ones((1, n))
+    G = np.random.default_rng(0).standard_normal((1, m, n))
+    h = np.ones((1, m))
+    with pytest.raises(ValueError):
+        cvxopt_b200.qp_batch(P, q, G, h)
