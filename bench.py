@@ -52,6 +52,58 @@ def make_problem(n, m, seed):
     return P, G, d, rng
 
 
+def make_qp(n, m, seed):
+    """full dense QP: P, q, G, h with a strictly feasible point"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    A0 = rng.standard_normal((n, n))
+    P = A0.T @ A0 / n + np.eye(n)
+    del A0
+    q = rng.standard_normal(n)
+    G = rng.standard_normal((m, n))
+    x0 = rng.standard_normal(n)
+    h = G @ x0 + rng.uniform(0.1, 1.1, m)
+    return P, q, G, h
+
+
+def run_ipm(n, m, seed, device):
+    """whole interior-point solve of one dense QP, device resident (cvxopt_b200.QPBatch, B=1)"""
+    import cvxopt_b200
+    P, q, G, h = make_qp(n, m, seed)
+    b = cvxopt_b200.QPBatch(1, n, m, device)
+    b.load(P[None], q[None], G[None], h[None])
+    b.solve()                      # warm-up (first-launch overheads, clocks)
+    t0 = time.perf_counter()
+    b.solve()
+    wall = (time.perf_counter() - t0) * 1e3
+    r, st = b.results(), b.stats()
+    b.close()
+    it = int(r["iterations"][0])
+    f_fac, f_sol, f_it = flops(n, m)
+    return {"n": n, "m": m, "iterations": it, "status": r["status"][0], "ms_total": st["solve_ms"],
+            "wall_ms": wall, "iters_per_s": (it + 1) / (st["solve_ms"] * 1e-3),
+            "primal_objective": float(r["primal objective"][0]),
+            "gflops": (it + 1) * f_it / (st["solve_ms"] * 1e-3) * 1e-9}
+
+
+def run_batch(nprob, n, m, device, rank, world):
+    """BASELINE config 4: nprob independent QPs sharded over the ranks (contiguous blocks)"""
+    import cvxopt_b200
+    lo, hi = cvxopt_b200.shard_bounds(nprob, world)[rank]
+    Ps, qs, Gs, hs = [], [], [], []
+    for k in range(lo, hi):
+        P, q, G, h = make_qp(n, m, k)
+        Ps.append(P); qs.append(q); Gs.append(G); hs.append(h)
+    b = cvxopt_b200.QPBatch(hi - lo, n, m, device)
+    b.load(np.stack(Ps), np.stack(qs), np.stack(Gs), np.stack(hs))
+    b.solve()
+    b.solve()
+    r, st = b.results(), b.stats()
+    b.close()
+    return {"problems": hi - lo, "ms": st["solve_ms"], "lockstep_iterations": st["lockstep_iterations"],
+            "iterations_sum": int(r["iterations"].sum()),
+            "all_optimal": bool(all(x == "optimal" for x in r["status"]))}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -193,6 +245,8 @@ def main():
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ipm", action="store_true", help="skip the full-IPM and batch extras")
+    ap.add_argument("--batch", type=int, default=512)
     args = ap.parse_args()
     if args.m <= 0:
         args.m = 2 * args.n
@@ -323,6 +377,32 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(args, P, G, d)
+    kkt.close()
+    del kkt, d_d, d_di, xs, zs
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.no_ipm:
+        # (ii) IPM iterations/s: a whole solve of the same-size QP, device resident
+        if rank == 0:
+            extras["ipm"] = run_ipm(n, m, args.seed, local_rank)
+        barrier()
+        # config 4: batch of independent QPs, strong scaling over the ranks
+        bres = run_batch(args.batch, 512, 1024, local_rank, rank, world)
+        t = torch.tensor([bres["ms"]], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([float(bres["iterations_sum"]), float(bres["problems"]), float(bres["all_optimal"])],
+                           dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            bf = flops(512, 1024)[2]
+            extras["batch"] = {"workload": "%d independent dense QPs n=512 m=1024, %d per GPU" % (args.batch, bres["problems"]),
+                               "ms": float(t.item()), "problems_per_s": args.batch / (float(t.item()) * 1e-3),
+                               "ipm_iterations_total": int(cnt[0].item()),
+                               "gflops": (cnt[0].item() + cnt[1].item()) * bf / (float(t.item()) * 1e-3) * 1e-9,
+                               "all_optimal": bool(cnt[2].item() == world), "scaling": "strong"}
+    if rank == 0:
+        out.update(extras)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -17,6 +17,7 @@
 //   per 128-row block, progress published through acquire/release flags so that the
 //   whole triangular solve is a single kernel (no per-block launches).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace cvxb {
 
@@ -39,8 +40,12 @@ constexpr int POTF2_SMEM = (NB * LDM + NB * SP + 4 * 80) * 8;
 // memory by recursive doubling (X21 = -X22 (L21 X11)) with DMMA tile products.
 __global__ void __launch_bounds__(256, 1)
 potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, int *info, int joff,
-                 long long sA, long long sInv) {
+                 long long sA, long long sInv, const double *Tprev, long long ldt,
+                 const double *invprev, unsigned long long *trace) {
     extern __shared__ __align__(16) double sm[];
+    if (trace && threadIdx.x == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[0] = t;
+    }
     A += (long long)blockIdx.x * sA; inv += (long long)blockIdx.x * sInv;
     invT += (long long)blockIdx.x * sInv; info += blockIdx.x;
     double *M = sm;                    // NB x LDM, column-major
@@ -50,35 +55,96 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
     const int wr = warp & 1, wc = warp >> 1;
     const int g4 = lane >> 2, t4 = lane & 3;
 
-    for (int e = tid; e < NB * NB; e += 256) {
-        int i = e & (NB - 1), k = e >> 7;
-        double v = (i == k) ? 1.0 : 0.0;
-        if (i < jb && k < jb && i >= k) v = A[i + (long long)k * lda];
-        M[i + k * LDM] = v;
-    }
-    __syncthreads();
     double acc[4][8][2];
+    // ---- optional prologue (look-ahead of the blocked factorisation): this diagonal block still
+    // misses the previous step's update.  Tprev = A(j, j-1) before its TRSM, invprev = inv(L_{j-1,j-1}):
+    //   Lt = Tprev * invprev'   (private copy of L(j, j-1)),   C -= Lt Lt'
+    // so the chain of diagonal factorisations never waits for the full-width TRSM / update.
+    if (Tprev != nullptr) {
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) acc[cf][rf][0] = acc[cf][rf][1] = 0.0;
+        const int kkmax = (wc + 1) * 8;                 // invprev[c, k] = 0 for k > c
+        const double *tp[8];
+        bool tv[8];
+#pragma unroll
+        for (int rf = 0; rf < 8; ++rf) {
+            const int r = wr * 64 + rf * 8 + g4;
+            tv[rf] = r < jb;
+            tp[rf] = Tprev + (tv[rf] ? r : 0) + (long long)t4 * ldt;
+        }
+        const double *ip = invprev + (wc * 32 + g4) + t4 * NB;
+#pragma unroll 2
+        for (int kk = 0; kk < kkmax; ++kk) {
+            double a[4], bfr[8];
+#pragma unroll
+            for (int cf = 0; cf < 4; ++cf) a[cf] = ip[cf * 8 + kk * 4 * NB];
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) bfr[rf] = tv[rf] ? tp[rf][(long long)kk * 4 * ldt] : 0.0;
+#pragma unroll
+            for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bfr[rf]);
+        }
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    M[(wr * 64 + rf * 8 + t4 * 2 + e) + (wc * 32 + cf * 8 + g4) * LDM] = acc[cf][rf][e];
+    }
+    // the block itself: straight into the fragment registers (identity padding beyond jb)
 #pragma unroll
     for (int cf = 0; cf < 4; ++cf)
 #pragma unroll
         for (int rf = 0; rf < 8; ++rf)
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-                acc[cf][rf][e] = M[(wr * 64 + rf * 8 + t4 * 2 + e) + (wc * 32 + cf * 8 + g4) * LDM];
+            for (int e = 0; e < 2; ++e) {
+                const int r = wr * 64 + rf * 8 + t4 * 2 + e, c = wc * 32 + cf * 8 + g4;
+                double v = (r == c) ? 1.0 : 0.0;
+                if (r < jb && c < jb && r >= c) v = A[r + (long long)c * lda];
+                acc[cf][rf][e] = v;
+            }
     __syncthreads();
-
-    for (int tq = 0; tq < NB / PB / 4; ++tq) {
+    if (Tprev != nullptr) {
+#pragma unroll 2
+        for (int kk = 0; kk < NB / 4; ++kk) {
+            double a[4], bfr[8];
 #pragma unroll
-      for (int tc = 0; tc < 4; ++tc) {     // tc is compile-time: fragment indices stay static
-        const int t = tq * 4 + tc;
+            for (int cf = 0; cf < 4; ++cf) a[cf] = -M[(wc * 32 + cf * 8 + g4) + (kk * 4 + t4) * LDM];
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) bfr[rf] = M[(wr * 64 + rf * 8 + g4) + (kk * 4 + t4) * LDM];
+#pragma unroll
+            for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) {
+                    if (wr * 64 + rf * 8 + 7 < wc * 32 + cf * 8) continue;   // strictly above the diagonal
+                    dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bfr[rf]);
+                }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll 1
+    for (int t = 0; t < NB / PB; ++t) {
+      {
         const int c0 = t * PB;
         // 1. owners of column block t publish it: P[r][k] = C[r, c0 + k]
-        if (wc == tq) {
-#pragma unroll
-            for (int rf = 0; rf < 8; ++rf)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    P[(wr * 64 + rf * 8 + t4 * 2 + e) * SP + g4] = acc[tc][rf][e];
+        //    (switch keeps the fragment index static without unrolling the whole step 4x)
+        if (wc == (t >> 2)) {
+#define CVXB_PUBLISH(CF)                                                          \
+    _Pragma("unroll") for (int rf = 0; rf < 8; ++rf)                              \
+        _Pragma("unroll") for (int e = 0; e < 2; ++e)                             \
+            P[(wr * 64 + rf * 8 + t4 * 2 + e) * SP + g4] = acc[CF][rf][e];
+            switch (t & 3) {
+                case 0: CVXB_PUBLISH(0) break;
+                case 1: CVXB_PUBLISH(1) break;
+                case 2: CVXB_PUBLISH(2) break;
+                default: CVXB_PUBLISH(3) break;
+            }
+#undef CVXB_PUBLISH
         }
         __syncthreads();
         // 2. 8x8 Cholesky of the diagonal block, redundantly in every warp.
@@ -261,6 +327,9 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
         inv[e] = (i >= k) ? M[i + k * LDM] : 0.0;
         invT[e] = (k >= i) ? M[k + i * LDM] : 0.0;     // invT[i + k*NB] = inv[k + i*NB]
     }
+    if (trace && threadIdx.x == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[1] = t;
+    }
 }
 
 // ---- blocked triangular solve with one right-hand side ------------------------
@@ -416,7 +485,10 @@ int chol_work_create(CholWork &w) {
     int least = 0, greatest = 0;
     CVXB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     CVXB_CUDA(cudaStreamCreateWithPriority(&w.panel_stream, cudaStreamNonBlocking, greatest));
+    CVXB_CUDA(cudaStreamCreateWithPriority(&w.trsm_stream, cudaStreamNonBlocking, greatest));
     CVXB_CUDA(cudaStreamCreateWithPriority(&w.update_stream, cudaStreamNonBlocking, least));
+    CVXB_CUDA(cudaEventCreateWithFlags(&w.ev_end_t, cudaEventDisableTiming));
+    w.r_valid[0] = w.r_valid[1] = -1;
     CVXB_CUDA(cudaEventCreateWithFlags(&w.ev_start, cudaEventDisableTiming));
     CVXB_CUDA(cudaEventCreateWithFlags(&w.ev_panel, cudaEventDisableTiming));
     CVXB_CUDA(cudaEventCreateWithFlags(&w.ev_rest, cudaEventDisableTiming));
@@ -440,6 +512,10 @@ int chol_work_create(CholWork &w) {
 void chol_work_destroy(CholWork &w) {
     if (w.panel_stream) cudaStreamDestroy(w.panel_stream);
     if (w.update_stream) cudaStreamDestroy(w.update_stream);
+    if (w.trsm_stream) cudaStreamDestroy(w.trsm_stream);
+    if (w.ev_end_t) cudaEventDestroy(w.ev_end_t);
+    for (auto *v : {&w.ev_dg, &w.ev_tr, &w.ev_c0, &w.ev_r})
+        for (cudaEvent_t e : *v) cudaEventDestroy(e);
     if (w.ev_start) cudaEventDestroy(w.ev_start);
     if (w.ev_panel) cudaEventDestroy(w.ev_panel);
     if (w.ev_rest) cudaEventDestroy(w.ev_rest);
@@ -453,6 +529,15 @@ void chol_work_destroy(CholWork &w) {
     w = CholWork();
 }
 
+// Look-ahead schedule (three streams, per-step events):
+//   D  (diag chain)   Dg(j): potf2_inv of block (j,j); for j>0 its prologue first applies the
+//                     step j-1 update to the block from the RAW tile A(j,j-1) and inv(j-1), so the
+//                     chain Dg(j-1) -> Dg(j) never waits for a full-width kernel.
+//   T  (panel)        Tr(j): Wp = A(j+1:, j) inv(j)'           needs Dg(j), C0(j-1)
+//                     C0(j): block column j+1 below the diagonal block -= Wp Wp'   needs R(j-1)
+//   U  (bulk)         R(j):  all later block columns (lower tiles) -= Wp Wp'        needs Tr(j)
+//   Dg(j) needs C0(j-2) and R(j-2) (they produced the tiles it reads).  L21 is copied from Wp
+//   back into A on D after Dg(j+1) has consumed the raw tile.
 int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_t st) {
     if (n <= 0) return 0;
     const int nblk = (n + NB - 1) / NB;
@@ -465,14 +550,23 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
         for (int i = 0; i < 2; ++i) CVXB_CUDA(cudaMalloc(&w.panel[i], (size_t)rows * NB * sizeof(double)));
         w.panel_rows = rows;
     }
+    while ((int)w.ev_dg.size() < nblk) {
+        cudaEvent_t e[4];
+        for (int i = 0; i < 4; ++i) CVXB_CUDA(cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming));
+        w.ev_dg.push_back(e[0]); w.ev_tr.push_back(e[1]); w.ev_c0.push_back(e[2]); w.ev_r.push_back(e[3]);
+    }
+    if (getenv("CVXB_TRACE") && !w.trace) {
+        CVXB_CUDA(cudaMalloc(&w.trace, 8 * 4096 * sizeof(unsigned long long)));
+    }
+    if (w.trace) CVXB_CUDA(cudaMemsetAsync(w.trace, 0, 8 * 4096 * sizeof(unsigned long long), st));
     const int ldw = w.panel_rows;
-    const int panel_tiles = NB / dmma_gemm_tile_cols();      // c tiles that make up the next panel
-    cudaStream_t P = w.panel_stream, U = w.update_stream;
+    const int panel_tiles = NB / dmma_gemm_tile_cols();      // c tiles that make up one block column
+    cudaStream_t D = w.panel_stream, T = w.trsm_stream, U = w.update_stream;
     CVXB_CUDA(cudaMemsetAsync(w.d_info, 0, sizeof(int), st));
     CVXB_CUDA(cudaEventRecord(w.ev_start, st));
-    CVXB_CUDA(cudaStreamWaitEvent(P, w.ev_start, 0));
+    CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_start, 0));
+    CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_start, 0));
     CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_start, 0));
-    bool have_rest = false;
     for (int jb = 0; jb < nblk; ++jb) {
         const int j = jb * NB;
         const int wj = (n - j < NB) ? (n - j) : NB;
@@ -480,48 +574,79 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
         double *Ajj = A + j + (long long)j * lda;
         double *invj = inv + (long long)jb * NB * NB;
         double *invTj = inv + (long long)(nblk + jb) * NB * NB;
-        potf2_inv_kernel<<<1, 256, POTF2_SMEM, P>>>(Ajj, lda, wj, invj, invTj, w.d_info, j, 0, 0);
+        // ---- D: diagonal block ----
+        if (jb >= 2) {
+            CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_c0[jb - 2], 0));
+            if (w.r_valid[(jb - 2) & 1] == jb - 2) CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_r[jb - 2], 0));
+        }
+        const double *Tprev = jb > 0 ? A + j + (long long)(j - NB) * lda : nullptr;
+        const double *invprev = jb > 0 ? inv + (long long)(jb - 1) * NB * NB : nullptr;
+        potf2_inv_kernel<<<1, 256, POTF2_SMEM, D>>>(Ajj, lda, wj, invj, invTj, w.d_info, j, 0, 0, Tprev,
+                                                     lda, invprev, w.trace ? w.trace + 8 * jb : nullptr);
         count_launch();
         CVXB_LAUNCH_CHECK();
+        CVXB_CUDA(cudaEventRecord(w.ev_dg[jb], D));
+        if (jb > 0) {
+            // L(j:, j-1) back into A, now that the raw tile has been consumed
+            const int jp = j - NB, mp = n - j;
+            CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_tr[jb - 1], 0));
+            CVXB_CUDA(cudaMemcpy2DAsync(A + j + (long long)jp * lda, (size_t)lda * sizeof(double),
+                                        w.panel[(jb - 1) & 1], (size_t)ldw * sizeof(double),
+                                        (size_t)mp * sizeof(double), NB, cudaMemcpyDeviceToDevice, D));
+        }
         if (m <= 0) break;
         double *A21 = Ajj + wj;
         double *A22 = A21 + (long long)wj * lda;
         double *Wp = w.panel[jb & 1];
-        {   // panel TRSM as a GEMM with the block inverse: Wp = A21 * inv(L11)'
-            // (out of place: the two 64-column tiles of a row block read all 128 columns)
+        // ---- T: panel TRSM as a GEMM with the block inverse (out of place) ----
+        CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_dg[jb], 0));
+        {
             GemmDesc g;
             g.M = m; g.N = wj; g.K = wj;
             g.X = A21; g.ldx = lda; g.x_kmajor = false;
             g.Y = invj; g.ldy = NB; g.y_kmajor = false;
             g.C = Wp; g.ldc = ldw;
-            CVXB_TRY(dmma_gemm(g, P));
+            g.trace = w.trace ? w.trace + 8 * jb + 2 : nullptr;
+            CVXB_TRY(dmma_gemm(g, T));
         }
-        CVXB_CUDA(cudaEventRecord(w.ev_panel, P));
-        GemmDesc u;
-        u.M = m; u.N = m; u.K = wj;
-        u.X = Wp; u.ldx = ldw; u.x_kmajor = false;
-        u.Y = Wp; u.ldy = ldw; u.y_kmajor = false;
-        u.D = A22; u.ldd = lda; u.C = A22; u.ldc = lda;
-        u.alpha = -1.0; u.beta = 1.0; u.lower_only = true;
-        // the next panel's columns first, on the panel stream
-        if (have_rest) CVXB_CUDA(cudaStreamWaitEvent(P, w.ev_rest, 0));
-        u.ct_begin = 0; u.ct_end = panel_tiles;
-        CVXB_TRY(dmma_gemm(u, P));
+        CVXB_CUDA(cudaEventRecord(w.ev_tr[jb], T));
+        // ---- T: next block column, rows below its diagonal block ----
+        const int wn = (m < NB) ? m : NB;          // width of block column jb+1
+        if (m > wn) {
+            if (jb >= 1 && w.r_valid[(jb - 1) & 1] == jb - 1) CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_r[jb - 1], 0));
+            GemmDesc c;
+            c.M = m - wn; c.N = wn; c.K = wj;
+            c.X = Wp + wn; c.ldx = ldw; c.x_kmajor = false;
+            c.Y = Wp; c.ldy = ldw; c.y_kmajor = false;
+            c.D = A22 + wn; c.ldd = lda; c.C = A22 + wn; c.ldc = lda;
+            c.alpha = -1.0; c.beta = 1.0;
+            c.trace = w.trace ? w.trace + 8 * jb + 4 : nullptr;
+            CVXB_TRY(dmma_gemm(c, T));
+        }
+        CVXB_CUDA(cudaEventRecord(w.ev_c0[jb], T));
+        // ---- U: the rest of the trailing matrix ----
         if (m > NB) {
-            CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_panel, 0));
+            CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_tr[jb], 0));
+            GemmDesc u;
+            u.M = m; u.N = m; u.K = wj;
+            u.X = Wp; u.ldx = ldw; u.x_kmajor = false;
+            u.Y = Wp; u.ldy = ldw; u.y_kmajor = false;
+            u.D = A22; u.ldd = lda; u.C = A22; u.ldc = lda;
+            u.alpha = -1.0; u.beta = 1.0; u.lower_only = true;
             u.ct_begin = panel_tiles; u.ct_end = 1 << 30;
+            u.trace = w.trace ? w.trace + 8 * jb + 6 : nullptr;
             CVXB_TRY(dmma_gemm(u, U));
-            CVXB_CUDA(cudaEventRecord(w.ev_rest, U));
-            have_rest = true;
+            CVXB_CUDA(cudaEventRecord(w.ev_r[jb], U));
+            w.r_valid[jb & 1] = jb;
         }
-        // L21 itself goes back into A (off the critical path of the next panel)
-        CVXB_CUDA(cudaMemcpy2DAsync(A21, (size_t)lda * sizeof(double), Wp, (size_t)ldw * sizeof(double),
-                                    (size_t)m * sizeof(double), wj, cudaMemcpyDeviceToDevice, P));
     }
-    CVXB_CUDA(cudaEventRecord(w.ev_end_p, P));
+    w.r_valid[0] = w.r_valid[1] = -1;
+    CVXB_CUDA(cudaEventRecord(w.ev_end_p, D));
     CVXB_CUDA(cudaEventRecord(w.ev_end_u, U));
+    CVXB_CUDA(cudaEventRecord(w.ev_end_t, T));
     CVXB_CUDA(cudaStreamWaitEvent(st, w.ev_end_p, 0));
     CVXB_CUDA(cudaStreamWaitEvent(st, w.ev_end_u, 0));
+    CVXB_CUDA(cudaStreamWaitEvent(st, w.ev_end_t, 0));
     return 0;
 }
 
@@ -580,7 +705,8 @@ int potrf_lower_batched(int n, double *A, int lda, long long sA, double *inv, lo
         double *Ajj = A + j + (long long)j * lda;
         double *invj = inv + (long long)jb * NB * NB;
         double *invTj = inv + (long long)(nblk + jb) * NB * NB;
-        potf2_inv_kernel<<<batch, 256, POTF2_SMEM, st>>>(Ajj, lda, wj, invj, invTj, d_info, j, sA, sInv);
+        potf2_inv_kernel<<<batch, 256, POTF2_SMEM, st>>>(Ajj, lda, wj, invj, invTj, d_info, j, sA, sInv, nullptr, 0,
+                                                        nullptr, nullptr);
         count_launch();
         CVXB_LAUNCH_CHECK();
         if (m <= 0) break;

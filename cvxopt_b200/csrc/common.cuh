@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "../../include/cvxopt_b200.h"
 
 namespace cvxb {
@@ -105,6 +106,8 @@ struct GemmDesc {
     long long sX = 0, sY = 0, sW = 0, sD = 0, sC = 0;
     // split-K remainder workspace (>= kNumSMs * 128*128 doubles) or nullptr to disable
     double *splitk_ws = nullptr;
+    // debug timeline (CVXB_TRACE): [0] = min CTA start, [1] = max CTA end (globaltimer ns)
+    unsigned long long *trace = nullptr;
 };
 int dmma_gemm(const GemmDesc &g, cudaStream_t st);
 size_t dmma_gemm_splitk_ws_doubles();   // workspace size for GemmDesc::splitk_ws
@@ -115,7 +118,12 @@ int dmma_gemm_tile_cols();              // width of a c tile (units of ct_begin 
 // info (device int) = first non-positive pivot (1-based) or 0.
 struct CholWork {
     cudaStream_t panel_stream = nullptr;   // high-priority: diagonal block, panel, next-panel update
+    cudaStream_t trsm_stream = nullptr;    // high-priority: panel TRSM + next block column update
     cudaStream_t update_stream = nullptr;  // low-priority: bulk trailing update
+    cudaEvent_t ev_end_t = nullptr;
+    std::vector<cudaEvent_t> ev_dg, ev_tr, ev_c0, ev_r;   // one per block step
+    unsigned long long *trace = nullptr;  // CVXB_TRACE=1: per step {Dg, Tr, C0, R} x {start, end}
+    int r_valid[2] = {-1, -1};            // which steps recorded ev_r (steps without bulk work do not)
     cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr, ev_end_p = nullptr,
                 ev_end_u = nullptr;
     int *d_info = nullptr;                // device flag

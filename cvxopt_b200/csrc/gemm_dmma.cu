@@ -44,6 +44,7 @@ constexpr int STAGE_DOUBLES = X_STAGE + Y_STAGE + BK;
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;      // 92544 B -> 2 CTAs / SM
 constexpr int TILE_ELEMS = BR * BC;
 constexpr int CTAS_PER_WAVE = 2 * kNumSMs;
+constexpr int SPLITK_WS_TILES = 4 * CTAS_PER_WAVE;   // split-K workspace capacity (tiles)
 
 struct KParams {
     int M, N, K;
@@ -62,6 +63,8 @@ struct KParams {
     int kchunk;             // K elements per split (multiple of BK)
     double *ws;
     int vec_c;              // C/D allow 16-byte accesses
+    int stagger_ns;         // > 0: short-K launch, offset the second CTA of each SM by this much
+    unsigned long long *trace;
 };
 
 // first r tile that intersects the lower triangle for c tile `tc`
@@ -143,6 +146,10 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
     const int wr = warp & 1, wc = warp >> 1;
     const int g4 = lane >> 2, t4 = lane & 3;
 
+    if (p.trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicCAS(p.trace, 0ULL, t);   // first CTA to start
+    }
     // ---- which unit am I? ----
     const int u = blockIdx.x;
     int tile, split = 0;
@@ -179,6 +186,33 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
     CopyPlan<YK, VEC, BC> py;
     px.init(Xt, p.ldx, nr, tid);
     py.init(Yt, p.ldy, nc, tid);
+
+    // Short-K launches (Cholesky trailing updates, K = 128): a tile's prologue/epilogue is as
+    // long as half its main loop, and the two CTAs that share an SM start together and stay in
+    // lock-step, so nothing overlaps (r01e profile: DMMA pipe 63 % busy).  (1) pull the D tile
+    // towards L2 now, so the epilogue's read-modify-write does not pay DRAM latency four times;
+    // (2) hold back the second CTA of every SM by half a tile so that one CTA's epilogue and
+    // prologue run under the other's DMMAs from then on.
+    if (p.stagger_ns > 0) {
+        if (p.beta != 0.0 && p.D != nullptr && !is_split) {
+            const double *Dt = p.D + b * p.sD + r0 + (long long)c0 * p.ldd;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int line = tid * 4 + i;               // 512 lines of 128 B in a 128x64 tile
+                const int col = line >> 3, seg = line & 7;
+                if (col < nc && seg * 16 < nr)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Dt + seg * 16 + (long long)col * p.ldd));
+            }
+        }
+        if (blockIdx.x >= (unsigned)kNumSMs && blockIdx.x < (unsigned)(2 * kNumSMs)) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(256);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < (unsigned long long)p.stagger_ns);
+        }
+    }
 
     double acc[4][8][2];
 #pragma unroll
@@ -280,27 +314,59 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
             }
         return;
     }
+    struct TraceEnd {
+        unsigned long long *tr; int tid;
+        __device__ ~TraceEnd() {
+            if (tr && tid == 0) {
+                unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                atomicMax(tr + 1, t);
+            }
+        }
+    } trace_end{p.trace, tid};
     double *C = p.C + b * p.sC;
     const double *D = p.D ? p.D + b * p.sD : nullptr;
     const bool diag = p.lower_only && (c0 + BC - 1 > r0);       // tile touches the diagonal
     const bool use_d = (p.beta != 0.0);
     const bool fast = p.vec_c && (nr == BR) && (nc == BC) && !diag;
     if (fast) {
-        // full interior tile: 16-byte accesses, all D loads of a column group in flight together
+        // full interior tile, 16-byte accesses
+        if (use_d) {
+            // read-modify-write epilogue: stage the whole D tile through the (now idle) pipeline
+            // buffers with one burst of cp.async — a single memory round trip with coalesced
+            // 1 KB column segments, instead of four dependent rounds of fragment-pattern loads
+            constexpr int LDT = BR + 8;                     // 136: conflict-free 16-byte fragment reads
+            static_assert(BC * LDT <= STAGES * STAGE_DOUBLES, "D tile must fit in the stage buffers");
+            __syncthreads();                                // every warp is done with the stages
+            const double *Dt = D + r0 + (long long)c0 * p.ldd;
+#pragma unroll 8
+            for (int i = 0; i < (BR * BC / 2) / THREADS; ++i) {
+                const int q = tid + i * THREADS;            // 16-byte piece index
+                const int col = q >> 6, rr = (q & 63) * 2;
+                cp_async16(smem + col * LDT + rr, Dt + rr + (long long)col * p.ldd, 16);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+#pragma unroll
+            for (int cf = 0; cf < 4; ++cf) {
+                const int cl = wc * 32 + cf * 8 + g4;
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) {
+                    const int rl = wr * 64 + rf * 8 + t4 * 2;
+                    const double2 dv = *reinterpret_cast<const double2 *>(smem + cl * LDT + rl);
+                    double2 v = make_double2(p.alpha * acc[cf][rf][0] + p.beta * dv.x,
+                                             p.alpha * acc[cf][rf][1] + p.beta * dv.y);
+                    *reinterpret_cast<double2 *>(C + (r0 + rl) + (long long)(c0 + cl) * p.ldc) = v;
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int cf = 0; cf < 4; ++cf) {
             const long long c = c0 + wc * 32 + cf * 8 + g4;
-            double2 dv[8];
-            if (use_d) {
-#pragma unroll
-                for (int rf = 0; rf < 8; ++rf)
-                    dv[rf] = *reinterpret_cast<const double2 *>(
-                        D + (r0 + wr * 64 + rf * 8 + t4 * 2) + c * p.ldd);
-            }
 #pragma unroll
             for (int rf = 0; rf < 8; ++rf) {
                 double2 v = make_double2(p.alpha * acc[cf][rf][0], p.alpha * acc[cf][rf][1]);
-                if (use_d) { v.x += p.beta * dv[rf].x; v.y += p.beta * dv[rf].y; }
                 *reinterpret_cast<double2 *>(C + (r0 + wr * 64 + rf * 8 + t4 * 2) + c * p.ldc) = v;
             }
         }
@@ -366,7 +432,7 @@ int launch_inst(const KParams &p, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
-size_t dmma_gemm_splitk_ws_doubles() { return (size_t)CTAS_PER_WAVE * TILE_ELEMS; }
+size_t dmma_gemm_splitk_ws_doubles() { return (size_t)SPLITK_WS_TILES * TILE_ELEMS; }
 int dmma_gemm_tile_cols() { return BC; }
 
 int dmma_gemm(const GemmDesc &g, cudaStream_t st) {
@@ -400,21 +466,35 @@ int dmma_gemm(const GemmDesc &g, cudaStream_t st) {
     // split-K of the remainder wave (deterministic: partials + ordered reduce)
     p.full_tiles = (int)T; p.S = 1; p.kchunk = g.K; p.ws = nullptr;
     if (g.splitk_ws && g.batch == 1 && g.K >= 1024) {
+        // the tiles of the last, partial wave are split along K so that the tail costs
+        // ceil(rem*S / wave) / S of a tile time instead of a whole one
         int full = (int)(T / CTAS_PER_WAVE) * CTAS_PER_WAVE;
         int rem = (int)T - full;
         if (rem > 0) {
-            int S = CTAS_PER_WAVE / rem;
             int maxS = g.K / 512;
-            if (S > maxS) S = maxS;
-            if (S >= 2) {
+            if (maxS > 18) maxS = 18;
+            const int cap_units = SPLITK_WS_TILES;           // workspace capacity in tiles
+            int bestS = 1;
+            double best = 1.0;
+            for (int S = 2; S <= maxS; ++S) {
+                if ((long long)rem * S > cap_units) break;
+                const double cost = (double)((rem * S + CTAS_PER_WAVE - 1) / CTAS_PER_WAVE) / S;
+                if (cost < best - 1e-9) { best = cost; bestS = S; }
+            }
+            if (bestS >= 2) {
                 p.full_tiles = full;
-                p.S = S;
-                int kc = (g.K + S - 1) / S;
+                p.S = bestS;
+                int kc = (g.K + bestS - 1) / bestS;
                 p.kchunk = ((kc + BK - 1) / BK) * BK;
                 p.ws = g.splitk_ws;
             }
         }
     }
+    // short-K, multi-wave launches: half of a tile's shared main-loop time (two CTAs share the
+    // DMMA pipe: ~2.1 us per 16-wide k step)
+    p.stagger_ns = 0;
+    p.trace = g.trace;
+    if (g.K <= 512 && T > CTAS_PER_WAVE) p.stagger_ns = ((g.K + BK - 1) / BK) * 1050;
     const int rem_tiles = (int)T - p.full_tiles;
     const int units = p.full_tiles + rem_tiles * p.S;
     dim3 grid(units, 1, g.batch);

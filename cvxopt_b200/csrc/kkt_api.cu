@@ -437,6 +437,12 @@ int cvxb_kkt_timer_stop(cvxb_kkt *k, double *ms) {
     *ms = t;
     return 0;
 }
+/* debug: copy the CVXB_TRACE timeline of the last potrf (8 values per block step) */
+int cvxb_kkt_trace(cvxb_kkt *k, unsigned long long *out, int nsteps) {
+    if (!k || !out || !k->cw.trace) return CVXB_E_ARG;
+    CVXB_CUDA(cudaMemcpy(out, k->cw.trace, (size_t)nsteps * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3) {
     if (!k || !ms3) return CVXB_E_ARG;
     ms3[0] = k->br[1]; ms3[1] = k->br[2]; ms3[2] = k->br[0];

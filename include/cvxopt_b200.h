@@ -108,6 +108,9 @@ int cvxb_kkt_last_ms(cvxb_kkt *k, double *factor_ms, double *solve_ms);
  * start records an event; stop records, synchronises and returns the elapsed ms */
 int cvxb_kkt_timer_start(cvxb_kkt *k);
 int cvxb_kkt_timer_stop(cvxb_kkt *k, double *ms);
+/* debug (env CVXB_TRACE=1): globaltimer timeline of the last Cholesky, 8 values per block step:
+ * {diag, trsm, next-column update, bulk update} x {start, end} in ns */
+int cvxb_kkt_trace(cvxb_kkt *k, unsigned long long *out, int nsteps);
 /* per-kernel-class CUDA-event breakdown of the last factor (syrk, potrf, scale) */
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3);
 
