@@ -46,6 +46,11 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
     if (trace && threadIdx.x == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[0] = t;
     }
+#define CVXB_STAMP(SLOT)                                                                    \
+    if (trace && threadIdx.x == 0) {                                                        \
+        unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));       \
+        trace[8 * 2048 + (SLOT)] = t_;                                                      \
+    }
     A += (long long)blockIdx.x * sA; inv += (long long)blockIdx.x * sInv;
     invT += (long long)blockIdx.x * sInv; info += blockIdx.x;
     double *M = sm;                    // NB x LDM, column-major
@@ -95,6 +100,7 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
                 for (int e = 0; e < 2; ++e)
                     M[(wr * 64 + rf * 8 + t4 * 2 + e) + (wc * 32 + cf * 8 + g4) * LDM] = acc[cf][rf][e];
     }
+    CVXB_STAMP(0)
     // the block itself: straight into the fragment registers (identity padding beyond jb)
 #pragma unroll
     for (int cf = 0; cf < 4; ++cf)
@@ -127,6 +133,7 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
         __syncthreads();
     }
 
+    CVXB_STAMP(1)
 #pragma unroll 1
     for (int t = 0; t < NB / PB; ++t) {
       {
@@ -241,6 +248,7 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
       }
     }
 
+    CVXB_STAMP(2)
     // ---- inverse of L in shared memory ----
     // base: the 16 8x8 diagonal blocks, one per half-warp; lane (lane&15) < 8 owns column j
     {
@@ -322,6 +330,7 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
             __syncthreads();
         }
     }
+    CVXB_STAMP(3)
     for (int e = tid; e < NB * NB; e += 256) {
         int i = e & (NB - 1), k = e >> 7;
         inv[e] = (i >= k) ? M[i + k * LDM] : 0.0;
