@@ -175,18 +175,24 @@ def run_reference(args, rank, world):
         for _ in range(2):
             x, z = matrix(rng.standard_normal(n)), matrix(rng.standard_normal(m))
             f(x, y, z)
-    for _ in range(args.warmup):
+    # a full-size reference step takes tens of seconds on the host (single-threaded glue in
+    # misc.kkt_chol.factor): bound the sample so the whole arm ends within a few minutes
+    est = 2.4e-11 * f_it                      # ~ seconds per step at the ~45 GF/s measured on this pool
+    steps_run = max(1, min(args.steps, int(60.0 / max(est, 1e-3)) or 1))
+    warm_run = max(1, min(args.warmup, int(30.0 / max(est, 1e-3)) or 1))
+    for _ in range(warm_run):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps_run):
         step()
     dt = time.perf_counter() - t0
-    ms = dt / args.steps * 1e3
+    ms = dt / steps_run * 1e3
     val = f_it / (ms * 1e-3) * 1e-9
     base.update({"value": val, "ms_per_step": ms,
                  "cpu_baseline": {"value": val, "unit": "GF/s", "cores": min(cores, 64), "kind": "reference",
                                   "sample": "%d full-size steps after %d warm-up (misc.kkt_chol, scipy-openblas)"
-                                            % (args.steps, args.warmup)},
+                                            % (steps_run, warm_run)},
+                 "steps_run": steps_run,
                  "e2e": {"value": val, "unit": "GF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
     print(json.dumps(base))
@@ -241,8 +247,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=8192)
-    ap.add_argument("--m", type=int, default=0)
+    ap.add_argument("--nvars", "--n", dest="n", type=int, default=8192)
+    ap.add_argument("--mrows", "--m", dest="m", type=int, default=0)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ipm", action="store_true", help="skip the full-IPM and batch extras")
@@ -373,7 +379,10 @@ def main():
                          "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
                          "peak_source": "measured DMMA.8x8x4 pipe rate on this pool (tools/fp64_peak.cu; "
                                         "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 = 35.4)",
-                         "traffic": None},
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
+                         # committed capture profiles/r01d_syrk_n8192_ncu_summary.md (n=8192 only)
+                         "traffic": (11.05e9 + 0.27e9) if (n == 8192 and m == 16384) else None,
+                         "algorithmic_bytes": 8.0 * m * n + 8.0 * n * n},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(args, P, G, d)
