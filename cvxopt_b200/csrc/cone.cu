@@ -311,6 +311,23 @@ __global__ void gemv_n_reduce_kernel(int nrows, int nchunks, const double *ws, c
     y[k] = (beta == 0.0) ? alpha * s : alpha * s + beta * y[k];
 }
 
+// dst (cols x rows, ld ldd) = src' where src is rows x cols (ld lds); 32x32 tiles through smem
+__global__ void transpose_kernel(const double *src, long long lds, double *dst, long long ldd,
+                                 int rows, int cols) {
+    __shared__ double t[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int cc = ty; cc < 32; cc += 8) {
+        int r = r0 + tx, c = c0 + cc;
+        t[cc][tx] = (r < rows && c < cols) ? src[r + (long long)c * lds] : 0.0;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        int c = c0 + tx, r = r0 + rr;           // dst[c, r] = src[r, c]
+        if (r < rows && c < cols) dst[c + (long long)r * ldd] = t[tx][rr];
+    }
+}
+
 __global__ void vec_mul_kernel(int n, const double *a, const double *b, double *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] * b[i];
@@ -441,6 +458,16 @@ int gemv_n(int nrows, int ncols, const double *A, long long lda, const double *w
     }
     dim3 rg((nrows + 255) / 256, bs.batch);
     gemv_n_reduce_kernel<<<rg, 256, 0, st>>>(nrows, ncols > 0 ? nch : 0, ws, w, alpha, beta, y, bs, sws);
+    count_launch();
+    CVXB_LAUNCH_CHECK();
+    return 0;
+}
+
+int transpose_copy(const double *src, long long lds, double *dst, long long ldd, int rows, int cols,
+                   cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;

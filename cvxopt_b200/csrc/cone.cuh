@@ -78,5 +78,8 @@ int gemv_n(int nrows, int ncols, const double *A, long long lda, const double *w
 int vec_mul(int n, const double *a, const double *b, double *out, cudaStream_t st);  // out = a.*b
 int vec_axpby(int n, double alpha, const double *x, double beta, double *y, cudaStream_t st);
 int symmetrize_lower(int n, double *A, long long lda, int batch, long long stride, cudaStream_t st);
+// dst (cols x rows) = src' for src rows x cols
+int transpose_copy(const double *src, long long lds, double *dst, long long ldd, int rows, int cols,
+                   cudaStream_t st);
 
 }  // namespace cvxb

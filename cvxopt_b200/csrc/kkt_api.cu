@@ -67,6 +67,17 @@ struct cvxb_kkt {
     int nrest = 0;
     double *Gunp = nullptr;      // unpacked scaled 's' rows (sums2 x n) — only when ns > 0
     double *Dfbuf = nullptr;     // mnl x n upload buffer
+    // equality constraints (p > 0), kkt_chol2-style elimination (reference misc.py:1464-1472):
+    double *Aeq = nullptr;       // p x n (ld lda_eq)
+    long long lda_eq = 0;
+    double *Asct = nullptr;      // n x p: L^{-1} A'
+    long long ldas = 0;
+    double *Kp = nullptr;        // p x p: Asct' Asct, then its Cholesky factor
+    long long ldkp = 0;
+    double *invp = nullptr;      // diagonal-block inverses of chol(Kp)
+    double *yd = nullptr;        // p
+    bool singular = false;       // first factorisation failed -> S += A'A from then on (misc.py:1433-1447)
+    bool first_factor = true;
     DevScaling W;
     double *bzp = nullptr, *zin = nullptr, *zt = nullptr, *xv = nullptr, *yv = nullptr;
     double *gemv_ws = nullptr;
@@ -138,11 +149,8 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     if (!out) { set_error("kkt_create: out is NULL"); return CVXB_E_ARG; }
     *out = nullptr;
     if (n < 0 || p < 0) { set_error("kkt_create: negative size"); return CVXB_E_ARG; }
-    if (p > 0) {
-        (void)A; (void)lda;
-        set_error("kkt_create: equality constraints (p > 0) are not built yet");
-        return CVXB_E_UNSUP;
-    }
+    if (p > 0 && (!A || lda < p)) { set_error("kkt_create: A must be p x n with lda >= p"); return CVXB_E_ARG; }
+    if (p > n) { set_error("kkt_create: Rank(A) < p (p > n)"); return CVXB_E_ARG; }
     CVXB_TRY(check_device(device));
     cvxb_kkt *k = new cvxb_kkt();
     k->device = device; k->n = n; k->p = p;
@@ -196,6 +204,17 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
         KCUDA(cudaMalloc(&k->swork, want * sizeof(double)));
     }
     if (c.mnl > 0) KCUDA(cudaMalloc(&k->Dfbuf, (size_t)c.mnl * nn * sizeof(double)));
+    if (p > 0) {
+        k->lda_eq = (p + 1) & ~1;
+        k->ldas = (n + 1) & ~1;
+        k->ldkp = (p + 1) & ~1;
+        KCUDA(cudaMalloc(&k->Aeq, (size_t)k->lda_eq * nn * sizeof(double)));
+        KCUDA(cudaMalloc(&k->Asct, (size_t)k->ldas * p * sizeof(double)));
+        KCUDA(cudaMalloc(&k->Kp, (size_t)k->ldkp * p * sizeof(double)));
+        KCUDA(cudaMalloc(&k->invp, (size_t)2 * ((p + NB - 1) / NB + 1) * NB * NB * sizeof(double)));
+        KCUDA(cudaMalloc(&k->yd, (size_t)p * sizeof(double)));
+        KTRY(upload_matrix(k->Aeq, k->lda_eq, A, lda, p, n, space, k->st));
+    }
     KTRY(k->W.alloc(c));
     const size_t cd = (size_t)(c.cdim > 0 ? c.cdim : 1);
     KCUDA(cudaMalloc(&k->bzp, cd * sizeof(double)));
@@ -203,7 +222,10 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     KCUDA(cudaMalloc(&k->zt, cd * sizeof(double)));
     KCUDA(cudaMalloc(&k->xv, nn * sizeof(double)));
     KCUDA(cudaMalloc(&k->yv, (cd > nn ? cd : nn) * sizeof(double)));
-    KCUDA(cudaMalloc(&k->gemv_ws, cd * (size_t)gemv_n_chunks(n) * sizeof(double)));
+    {
+        size_t w1 = cd * (size_t)gemv_n_chunks(n), w2 = nn * (size_t)gemv_n_chunks(p > 0 ? p : 1);
+        KCUDA(cudaMalloc(&k->gemv_ws, (w1 > w2 ? w1 : w2) * sizeof(double)));
+    }
     KCUDA(cudaStreamSynchronize(k->st));
 #undef KTRY
 #undef KCUDA
@@ -216,7 +238,7 @@ void cvxb_kkt_destroy(cvxb_kkt *k) {
     cudaSetDevice(k->device);
     if (k->st) cudaStreamSynchronize(k->st);
     if (k->own_G && k->G) cudaFree(const_cast<double *>(k->G));
-    double *bufs[] = {k->Hres, k->Hbuf, k->Kmat, k->inv, k->Gs, k->Gunp, k->Dfbuf, k->bzp,
+    double *bufs[] = {k->Aeq, k->Asct, k->Kp, k->invp, k->yd, k->Hres, k->Hbuf, k->Kmat, k->inv, k->Gs, k->Gunp, k->Dfbuf, k->bzp,
                       k->zin, k->zt, k->xv, k->yv, k->gemv_ws, k->swork};
     for (double *b : bufs) if (b) cudaFree(b);
     k->W.destroy();
@@ -293,41 +315,104 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
         CVXB_TRY(pack_s(c, k->Gunp, c.sums2, k->Gs + c.mnl + c.sumq, k->ldgs, n, false, st));
     }
     CVXB_CUDA(cudaEventRecord(k->e1, st));
-    // ---- K = H + G_l' diag(di^2) G_l + Gs' Gs   (lower triangle) ----
-    bool have = false;
-    if (c.ml > 0 && n > 0) {
-        GemmDesc g;
-        g.M = n; g.N = n; g.K = c.ml;
-        g.X = k->G + c.mnl; g.ldx = (int)k->ldg; g.x_kmajor = true;
-        g.Y = g.X; g.ldy = g.ldx; g.y_kmajor = true;
-        g.w = k->W.di2;
-        g.D = Hptr; g.ldd = (int)ldH; g.beta = 1.0;
-        g.C = k->Kmat; g.ldc = (int)ldk;
-        g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
-        CVXB_TRY(dmma_gemm(g, st));
-        have = true;
-    }
-    if (k->nrest > 0 && n > 0) {
-        GemmDesc g;
-        g.M = n; g.N = n; g.K = k->nrest;
-        g.X = k->Gs; g.ldx = (int)k->ldgs; g.x_kmajor = true;
-        g.Y = g.X; g.ldy = g.ldx; g.y_kmajor = true;
-        g.D = have ? k->Kmat : Hptr; g.ldd = have ? (int)ldk : (int)ldH; g.beta = 1.0;
-        g.C = k->Kmat; g.ldc = (int)ldk;
-        g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
-        CVXB_TRY(dmma_gemm(g, st));
-        have = true;
-    }
-    if (!have && n > 0) {
-        if (!Hptr) { set_error("factor: no cone rows and no H: KKT matrix is singular"); return 1; }
-        CVXB_TRY(upload_matrix(k->Kmat, ldk, Hptr, ldH, n, n, CVXB_DEVICE, st));
-    }
-    CVXB_CUDA(cudaEventRecord(k->e2, st));
-    // ---- Cholesky ----
-    CVXB_TRY(potrf_lower(n, k->Kmat, (int)ldk, k->inv, k->cw, st));
-    CVXB_CUDA(cudaEventRecord(k->e3, st));
+    // ---- K = H + G_l' diag(di^2) G_l + Gs' Gs (+ A'A)  (lower triangle), then Cholesky ----
     int info = 0;
-    CVXB_CUDA(cudaMemcpyAsync(&info, k->cw.d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    auto assemble_and_factor = [&](bool add_ata) -> int {
+        bool have = false;
+        if (c.ml > 0 && n > 0) {
+            GemmDesc g;
+            g.M = n; g.N = n; g.K = c.ml;
+            g.X = k->G + c.mnl; g.ldx = (int)k->ldg; g.x_kmajor = true;
+            g.Y = g.X; g.ldy = g.ldx; g.y_kmajor = true;
+            g.w = k->W.di2;
+            g.D = Hptr; g.ldd = (int)ldH; g.beta = 1.0;
+            g.C = k->Kmat; g.ldc = (int)ldk;
+            g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
+            CVXB_TRY(dmma_gemm(g, st));
+            have = true;
+        }
+        if (k->nrest > 0 && n > 0) {
+            GemmDesc g;
+            g.M = n; g.N = n; g.K = k->nrest;
+            g.X = k->Gs; g.ldx = (int)k->ldgs; g.x_kmajor = true;
+            g.Y = g.X; g.ldy = g.ldx; g.y_kmajor = true;
+            g.D = have ? k->Kmat : Hptr; g.ldd = have ? (int)ldk : (int)ldH; g.beta = 1.0;
+            g.C = k->Kmat; g.ldc = (int)ldk;
+            g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
+            CVXB_TRY(dmma_gemm(g, st));
+            have = true;
+        }
+        if (add_ata && k->p > 0 && n > 0) {
+            GemmDesc g;                                   // S += A'A   (misc.py:1440)
+            g.M = n; g.N = n; g.K = k->p;
+            g.X = k->Aeq; g.ldx = (int)k->lda_eq; g.x_kmajor = true;
+            g.Y = g.X; g.ldy = g.ldx; g.y_kmajor = true;
+            g.D = have ? k->Kmat : Hptr; g.ldd = have ? (int)ldk : (int)ldH; g.beta = 1.0;
+            g.C = k->Kmat; g.ldc = (int)ldk;
+            g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
+            CVXB_TRY(dmma_gemm(g, st));
+            have = true;
+        }
+        if (!have && n > 0) {
+            if (!Hptr) { set_error("factor: no cone rows and no H: KKT matrix is singular"); return 1; }
+            CVXB_TRY(upload_matrix(k->Kmat, ldk, Hptr, ldH, n, n, CVXB_DEVICE, st));
+        }
+        CVXB_CUDA(cudaEventRecord(k->e2, st));
+        CVXB_TRY(potrf_lower(n, k->Kmat, (int)ldk, k->inv, k->cw, st));
+        CVXB_CUDA(cudaMemcpyAsync(&info, k->cw.d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CVXB_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    };
+    CVXB_TRY(assemble_and_factor(k->singular));
+    if (info > 0 && k->p > 0 && k->first_factor && !k->singular) {
+        // S is singular on the first call: switch to S + A'A for the rest of the solve
+        k->singular = true;
+        info = 0;
+        CVXB_TRY(assemble_and_factor(true));
+    }
+    k->first_factor = false;
+    if (info == 0 && k->p > 0) {
+        // Asct := L^{-1} A'  (blocked forward substitution with the diagonal-block inverses),
+        // Kp := Asct' Asct,  Kp = Lp Lp'                               (misc.py:1464-1472)
+        const int p = k->p;
+        CVXB_TRY(transpose_copy(k->Aeq, k->lda_eq, k->Asct, k->ldas, p, n, st));
+        const int nblk = (n + NB - 1) / NB;
+        for (int jb = 0; jb < nblk; ++jb) {
+            const int j = jb * NB;
+            const int wj = (n - j < NB) ? (n - j) : NB;
+            const int mrem = n - j - wj;
+            double *Bj = k->Asct + j;
+            {   // X_j = inv_jj * B_j   (in place: one tile owns its columns)
+                GemmDesc g;
+                g.M = wj; g.N = p; g.K = wj;
+                g.X = k->inv + (long long)jb * NB * NB; g.ldx = NB; g.x_kmajor = false;
+                g.Y = Bj; g.ldy = (int)k->ldas; g.y_kmajor = true;
+                g.C = Bj; g.ldc = (int)k->ldas;
+                CVXB_TRY(dmma_gemm(g, st));
+            }
+            if (mrem > 0) {   // B[j+1:, :] -= L[j+1:, j] X_j
+                GemmDesc g;
+                g.M = mrem; g.N = p; g.K = wj;
+                g.X = k->Kmat + (j + wj) + (long long)j * ldk; g.ldx = (int)ldk; g.x_kmajor = false;
+                g.Y = Bj; g.ldy = (int)k->ldas; g.y_kmajor = true;
+                g.D = Bj + wj; g.ldd = (int)k->ldas; g.C = Bj + wj; g.ldc = (int)k->ldas;
+                g.alpha = -1.0; g.beta = 1.0;
+                CVXB_TRY(dmma_gemm(g, st));
+            }
+        }
+        {
+            GemmDesc g;
+            g.M = p; g.N = p; g.K = n;
+            g.X = k->Asct; g.ldx = (int)k->ldas; g.x_kmajor = true;
+            g.Y = k->Asct; g.ldy = (int)k->ldas; g.y_kmajor = true;
+            g.C = k->Kp; g.ldc = (int)k->ldkp; g.lower_only = true;
+            CVXB_TRY(dmma_gemm(g, st));
+        }
+        CVXB_TRY(potrf_lower(p, k->Kp, (int)k->ldkp, k->invp, k->cw, st));
+        CVXB_CUDA(cudaMemcpyAsync(&info, k->cw.d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CVXB_CUDA(cudaStreamSynchronize(st));
+    }
+    CVXB_CUDA(cudaEventRecord(k->e3, st));
     CVXB_CUDA(cudaStreamSynchronize(st));
     float t;
     cudaEventElapsedTime(&t, k->e0, k->e3); k->factor_ms = t;
@@ -346,7 +431,6 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
 int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
     if (!k->factored) { set_error("solve called before a successful factor"); return CVXB_E_ARG; }
-    (void)y;   // p == 0
     CVXB_CUDA(cudaSetDevice(k->device));
     const ConeLayout &c = k->cone;
     const int n = k->n;
@@ -354,11 +438,13 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     const long long ldk = kkt_ldk(k);
     const int nlq = c.mnl + c.ml + c.sumq;     // rows that are identical packed / unpacked
     CVXB_CUDA(cudaEventRecord(k->e0, st));
-    double *xd = x, *zd = z;
+    double *xd = x, *zd = z, *ydv = y;
+    if (k->p > 0 && !y) { set_error("solve: y is required when p > 0"); return CVXB_E_ARG; }
     if (space != CVXB_DEVICE) {
         CVXB_TRY(xfer_vec(k->xv, x, n, CVXB_HOST, true, st));
         CVXB_TRY(xfer_vec(k->zin, z, c.cdim, CVXB_HOST, true, st));
         xd = k->xv; zd = k->zin;
+        if (k->p > 0) { CVXB_TRY(xfer_vec(k->yd, y, k->p, CVXB_HOST, true, st)); ydv = k->yd; }
     }
     // bzp := pack(W^{-T} bz)                                   (misc.py:1306-1307)
     if (c.mnl > 0) CVXB_TRY(scale_rows(zd, c.cdim, k->bzp, c.cdim, c.mnl, 1, k->W.dnli, st));
@@ -378,8 +464,20 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     if (k->nrest - c.mnl > 0)
         CVXB_TRY(gemv_t(k->nrest - c.mnl, n, k->Gs + c.mnl, k->ldgs, nullptr,
                         k->bzp + c.mnl + c.ml, 1.0, 1.0, xd, st));
-    // x := K^{-1} x                                               (misc.py:1327)
-    CVXB_TRY(potrs_lower(n, k->Kmat, (int)ldk, k->inv, xd, k->cw, st));
+    if (k->p == 0) {
+        // x := K^{-1} x                                           (misc.py:1327)
+        CVXB_TRY(potrs_lower(n, k->Kmat, (int)ldk, k->inv, xd, k->cw, st));
+    } else {
+        // kkt_chol2-style elimination of the equality constraints  (misc.py:1526-1558)
+        const int p = k->p;
+        if (k->singular)      // x += A' by
+            CVXB_TRY(gemv_t(p, n, k->Aeq, k->lda_eq, nullptr, ydv, 1.0, 1.0, xd, st));
+        CVXB_TRY(trsv_lower(n, k->Kmat, (int)ldk, k->inv, xd, false, k->cw, st));          // x := L^{-1} x
+        CVXB_TRY(gemv_t(n, p, k->Asct, k->ldas, nullptr, xd, 1.0, -1.0, ydv, st));         // y := Asct' x - y
+        CVXB_TRY(potrs_lower(p, k->Kp, (int)k->ldkp, k->invp, ydv, k->cw, st));            // y := Kp^{-1} y
+        CVXB_TRY(gemv_n(n, p, k->Asct, k->ldas, nullptr, ydv, -1.0, 1.0, xd, k->gemv_ws, st));   // x -= Asct y
+        CVXB_TRY(trsv_lower(n, k->Kmat, (int)ldk, k->inv, xd, true, k->cw, st));           // x := L^{-T} x
+    }
     // bzp := Gs x - bzp                                           (misc.py:1344)
     if (c.ml > 0)
         CVXB_TRY(gemv_n(c.ml, n, k->G + c.mnl, k->ldg, k->W.di, xd, 1.0, -1.0, k->bzp + c.mnl,
@@ -397,6 +495,7 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     if (space != CVXB_DEVICE) {
         CVXB_TRY(xfer_vec(x, k->xv, n, CVXB_HOST, false, st));
         CVXB_TRY(xfer_vec(z, k->zin, c.cdim, CVXB_HOST, false, st));
+        if (k->p > 0) CVXB_TRY(xfer_vec(y, k->yd, k->p, CVXB_HOST, false, st));
     }
     CVXB_CUDA(cudaEventRecord(k->e1, st));
     CVXB_CUDA(cudaStreamSynchronize(st));

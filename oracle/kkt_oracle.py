@@ -218,7 +218,13 @@ def _symL(x, m):
 
 # --------------------------------------------------------------------------- kkt_chol
 class KktChol:
-    """misc.kkt_chol for p == 0 (misc.py:1213-1349): factor(W, H, Df) -> solve(x, y, z)."""
+    """misc.kkt_chol (misc.py:1213-1349): factor(W, H, Df) -> solve(x, y, z).
+
+    p == 0 follows kkt_chol line by line.  For p > 0 the equality constraints are eliminated
+    with the Schur complement K = A S^{-1} A' of kkt_chol2 (misc.py:1464-1565, including its
+    `S += A'A` fallback when S is singular, :1433-1447) instead of kkt_chol's QR of A'
+    (:1244-1250, 1278-1339): the two are the same linear system; tests pin this class to the
+    reference's QR-based kkt_chol."""
 
     def __init__(self, G, dims, A=None, mnl=0):
         self.G = np.asfortranarray(np.asarray(G, dtype=float))
@@ -226,8 +232,11 @@ class KktChol:
         self.mnl = mnl
         self.n = self.G.shape[1]
         _, _, _, self.cdim, self.cdim_pckd = cone_sizes(dims, mnl)
+        self.A = None
         if A is not None and np.asarray(A).shape[0] > 0:
-            raise NotImplementedError("oracle restatement covers p == 0")
+            self.A = np.asarray(A, dtype=float)
+        self.singular = False
+        self.first = True
 
     def factor(self, W, H=None, Df=None):
         n, mnl = self.n, self.mnl
@@ -241,20 +250,46 @@ class KktChol:
         K = Gp.T @ Gp                                                # blas.syrk trans='T'  :1275
         if H is not None:
             K = K + np.tril(np.asarray(H)) + np.tril(np.asarray(H), -1).T   # :1276-1277
+        if self.A is not None and self.singular:
+            K = K + self.A.T @ self.A
         try:
             L = np.linalg.cholesky(K)                                # lapack.potrf  :1282
         except np.linalg.LinAlgError:
-            raise ArithmeticError("potrf: not positive definite")
+            if self.A is not None and self.first and not self.singular:
+                self.singular = True                                 # misc.py:1433-1447
+                K = K + self.A.T @ self.A
+                try:
+                    L = np.linalg.cholesky(K)
+                except np.linalg.LinAlgError:
+                    raise ArithmeticError("potrf: not positive definite")
+            else:
+                raise ArithmeticError("potrf: not positive definite")
+        self.first = False
+        if self.A is not None:
+            self.Asct = sla.solve_triangular(L, self.A.T, lower=True)    # :1470
+            try:
+                self.Lp = np.linalg.cholesky(self.Asct.T @ self.Asct)    # :1471-1472
+            except np.linalg.LinAlgError:
+                raise ArithmeticError("potrf: not positive definite")
         self.Gs, self.L, self.W = Gp, L, W
         return self.solve
 
     def solve(self, x, y, z):
-        """In place (bx, by, bz) -> (ux, uy, W uz).  misc.py:1284-1345"""
+        """In place (bx, by, bz) -> (ux, uy, W uz).  misc.py:1284-1345 / 1489-1563"""
         zc = z.reshape(-1, 1)
         scale(zc, self.W, trans="T", inverse="I")                    # :1306
         bzp = np.zeros(self.cdim_pckd)
         pack(z, bzp, self.dims, self.mnl)                            # :1307
         x += self.Gs.T @ bzp                                         # :1311
-        x[:] = sla.cho_solve((self.L, True), x)                      # :1327
+        if self.A is None:
+            x[:] = sla.cho_solve((self.L, True), x)                  # :1327
+        else:
+            if self.singular:
+                x += self.A.T @ y                                    # misc.py:1526-1527
+            x[:] = sla.solve_triangular(self.L, x, lower=True)       # :1529
+            y[:] = self.Asct.T @ x - y                               # :1541
+            y[:] = sla.cho_solve((self.Lp, True), y)                 # :1543
+            x -= self.Asct @ y                                       # :1553
+            x[:] = sla.solve_triangular(self.L, x, lower=True, trans="T")   # :1555
         bzp = self.Gs @ x - bzp                                      # :1344
         unpack(bzp, z, self.dims, self.mnl)                          # :1345

@@ -76,6 +76,38 @@ def test_mixed_cones():
     run_case({"l": 5, "q": [4], "s": [3]}, 3, 12, with_H=False)
 
 
+@pytest.mark.parametrize("dims,n,p,with_H", [
+    ({"l": 300, "q": [], "s": []}, 150, 20, True),
+    ({"l": 40, "q": [9, 30], "s": [7]}, 60, 5, True),
+    ({"l": 500, "q": [], "s": []}, 300, 130, False),       # p spans two 128-blocks
+    ({"l": 20, "q": [], "s": []}, 50, 35, False),          # S singular -> S + A'A fallback
+])
+def test_equality_constraints(dims, n, p, with_H):
+    """p > 0: (ux, uy, W uz) vs the oracle (which is pinned to the reference's QR-based kkt_chol)."""
+    import cvxopt_b200
+    rng = np.random.Generator(np.random.PCG64(77))
+    K = cone_dim(dims)
+    G = np.asfortranarray(rng.standard_normal((K, n)))
+    A = np.asfortranarray(rng.standard_normal((p, n)))
+    H = None
+    if with_H:
+        B = rng.standard_normal((n, n))
+        H = np.asfortranarray(B @ B.T / n + np.eye(n))
+    W, _ = random_scaling(dims, seed=8)
+    fac = cvxopt_b200.kkt_chol(G, dims, A)
+    solve = fac(W, H) if with_H else fac(W)
+    f_or = ko.KktChol(G, dims, A).factor(W, H)
+    for rep in range(2):
+        x, y, z = rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(K)
+        xo, yo, zo = x.copy(), y.copy(), z.copy()
+        solve(x, y, z)
+        f_or(xo, yo, zo)
+        assert relerr(x, xo) < 1e-9, relerr(x, xo)
+        assert relerr(y, yo) < 1e-9, relerr(y, yo)
+        assert relerr(packed(z, dims), packed(zo, dims)) < 1e-9
+    fac.close()
+
+
 def test_indefinite_raises_arithmetic_error():
     import cvxopt_b200
     n = 40

@@ -105,6 +105,37 @@ def test_kkt_chol_matches_reference(ref, dims):
     np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("dims", DIMS)
+@pytest.mark.parametrize("with_H", [True, False])
+def test_kkt_chol_with_equalities_matches_reference(ref, dims, with_H):
+    """p > 0: the oracle's Schur-complement elimination vs the reference's QR-based kkt_chol."""
+    from cvxopt import misc
+    n, p = 7, 3
+    rng = np.random.Generator(np.random.PCG64(31))
+    K = cone_dim(dims)
+    G = np.asfortranarray(rng.standard_normal((K, n)))
+    A = np.asfortranarray(rng.standard_normal((p, n)))
+    B = rng.standard_normal((n, n))
+    H = np.asfortranarray(B @ B.T + np.eye(n)) if with_H else None
+    W, _ = random_scaling(dims, seed=3)
+    if K < n and H is None:
+        pytest.skip("singular even with A'A")
+    f_or = ko.KktChol(G, dims, A).factor(W, H)
+    fr = misc.kkt_chol(ref.matrix(G), dims, ref.matrix(A))
+    f_ref = fr(to_ref_W(ref, W), ref.matrix(H)) if with_H else fr(to_ref_W(ref, W))
+    x, y, z = rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(K)
+    xr, yr, zr = ref.matrix(x), ref.matrix(y), ref.matrix(z)
+    f_or(x, y, z)
+    f_ref(xr, yr, zr)
+    np.testing.assert_allclose(x, np.array(xr).ravel(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(y, np.array(yr).ravel(), rtol=1e-9, atol=1e-11)
+    _, _, _, _, cp = ko.cone_sizes(dims)
+    a, b = np.zeros(cp), np.zeros(cp)
+    ko.pack(z, a, dims)
+    ko.pack(np.array(zr).ravel(), b, dims)
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-11)
+
+
 def test_reference_known_answer_coneqp(ref):
     """reference tests/test_examples.py:27-29 (examples/doc/chap8/coneqp.py): the only
     reference test whose numbers flow through kkt_chol."""

@@ -150,3 +150,24 @@ def test_device_operators_G_P(ref):
     b = solvers.coneqp(Pm, qm, Gm, hm, dims, kktsolver="chol")
     assert a["status"] == b["status"] == "optimal" and a["iterations"] == b["iterations"]
     np.testing.assert_allclose(a["primal objective"], b["primal objective"], rtol=1e-8)
+
+
+def test_qp_with_equality_constraints(ref):
+    """solvers.qp(P, q, G, h, A, b, kktsolver=...) — p > 0 through the plugin."""
+    import cvxopt_b200
+    from cvxopt import matrix, solvers
+    n, m, p = 90, 200, 12
+    P, q, G, h = dense_qp(n, m, seed=21)
+    rng = np.random.Generator(np.random.PCG64(5))
+    A = rng.standard_normal((p, n))
+    x0 = np.linalg.lstsq(G, h - 1.0, rcond=None)[0]
+    b = A @ np.zeros(n)        # x = 0 is feasible for A x = b; G 0 = 0 <= h requires h > 0
+    h = np.abs(h) + 1.0
+    Pm, qm, Gm, hm, Am, bm = matrix(P), matrix(q), matrix(G), matrix(h), matrix(A), matrix(b)
+    f = cvxopt_b200.kkt_chol(Gm, {"l": m, "q": [], "s": []}, Am, H=Pm)
+    a = solvers.qp(Pm, qm, Gm, hm, Am, bm, kktsolver=lambda W: f(W))
+    r = solvers.qp(Pm, qm, Gm, hm, Am, bm, kktsolver="chol")
+    assert a["status"] == r["status"] == "optimal" and a["iterations"] == r["iterations"]
+    np.testing.assert_allclose(a["primal objective"], r["primal objective"], rtol=1e-8)
+    np.testing.assert_allclose(np.array(a["x"]), np.array(r["x"]), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(np.array(a["y"]), np.array(r["y"]), rtol=1e-5, atol=1e-7)
