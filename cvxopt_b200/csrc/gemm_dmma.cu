@@ -223,6 +223,9 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
         for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int ktiles = (kend - kbeg + BK - 1) / BK;
+    // lower-triangular outputs: a warp whose whole block is above the diagonal only helps with the
+    // copies (matters for small n / batched SYRKs where a quarter of the tiles straddle the diagonal)
+    const bool warp_idle = p.lower_only && (r0 + wr * 64 + 63 < c0 + wc * 32);
 
     auto load_stage = [&](int kt, int stage) {
         double *sx = smem + stage * STAGE_DOUBLES;
@@ -262,6 +265,12 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         const double *st = smem + (kt % STAGES) * STAGE_DOUBLES;
+        if (warp_idle) {            // this warp's 64x32 block lies strictly above the diagonal
+            const int nk = kt + STAGES - 1;
+            if (nk < ktiles) load_stage(nk, nk % STAGES);
+            cp_async_commit();
+            continue;
+        }
         // fragments of kk = 0 first, so their latency overlaps the prefetch issue below
         double a[2][4], bf[2][8];
 #pragma unroll
