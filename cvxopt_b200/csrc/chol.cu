@@ -28,6 +28,29 @@ constexpr int SP = 12;                 // row stride (doubles) of the panel buff
 constexpr int LDM = NB + 4;            // column stride (doubles) of the shared-memory block
 constexpr int POTF2_SMEM = (NB * LDM + NB * SP + 4 * 80) * 8;
 
+// acc[cf][rf] -= sum_k Lt[c, k] Lt[r, k] over k = 0..127 for the tiles rf >= S_cf of each column
+// fragment cf (Lt in shared memory, column-major with stride LDM; Ma/Mb already offset by lane)
+template <int PAT>      // 0: every tile, 1: rf >= cf, 2: rf >= 4 + cf
+__device__ __forceinline__ void sym_update(double (&acc)[4][8][2], const double *Ma, const double *Mb) {
+#pragma unroll 2
+    for (int kk = 0; kk < NB / 4; ++kk) {
+        double a[4], bfr[8];
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) a[cf] = -Ma[cf * 8 + kk * 4 * LDM];
+#pragma unroll
+        for (int rf = 0; rf < 8; ++rf) bfr[rf] = Mb[rf * 8 + kk * 4 * LDM];
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) {
+                constexpr bool dummy = true; (void)dummy;
+                if (PAT == 1 && rf < cf) continue;           // compile-time after unrolling
+                if (PAT == 2 && rf < 4 + cf) continue;
+                dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bfr[rf]);
+            }
+    }
+}
+
 // Factor the jb x jb diagonal block at A (lower) in place, write inv(L) (NB x NB,
 // ld NB, zero upper, identity padding beyond jb) to inv.
 //
@@ -57,7 +80,11 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
     double *P = M + NB * LDM;          // NB x SP, row-major panel
     double *Dw = P + NB * SP;          // 4 private copies of the 8x8 factor (+ reciprocal diagonal)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wr = warp & 1, wc = warp >> 1;
+    // Warp -> 64x32 fragment block.  Only the lower triangle is live, so the blocks carry very
+    // different amounts of DMMA work; warps w and w+4 share an SM sub-partition, so pair a heavy
+    // block with a light one: SMSP0 (1,0)+(0,2), SMSP1 (1,1)+(0,3), SMSP2 (1,2)+(0,1), SMSP3 (0,0)+(1,3)
+    const int role = (0x72640531 >> (warp * 4)) & 7;     // role = wr + 2*wc, one nibble per warp
+    const int wr = role & 1, wc = role >> 1;
     const int g4 = lane >> 2, t4 = lane & 3;
 
     double acc[4][8][2];
@@ -114,25 +141,19 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
                 acc[cf][rf][e] = v;
             }
     __syncthreads();
+    CVXB_STAMP(4)
     if (Tprev != nullptr) {
-#pragma unroll 2
-        for (int kk = 0; kk < NB / 4; ++kk) {
-            double a[4], bfr[8];
-#pragma unroll
-            for (int cf = 0; cf < 4; ++cf) a[cf] = -M[(wc * 32 + cf * 8 + g4) + (kk * 4 + t4) * LDM];
-#pragma unroll
-            for (int rf = 0; rf < 8; ++rf) bfr[rf] = M[(wr * 64 + rf * 8 + g4) + (kk * 4 + t4) * LDM];
-#pragma unroll
-            for (int cf = 0; cf < 4; ++cf)
-#pragma unroll
-                for (int rf = 0; rf < 8; ++rf) {
-                    if (wr * 64 + rf * 8 + 7 < wc * 32 + cf * 8) continue;   // strictly above the diagonal
-                    dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bfr[rf]);
-                }
-        }
+        // which 8x8 tiles of this warp's 64x32 block touch the lower triangle depends only on
+        // d = wc - 2*wr: all (d < 0), rf >= cf (d == 0), rf >= 4 + cf (d == 1), none (d > 1).
+        // Static patterns keep the DMMA stream free of per-tile branches.
+        const int d = wc - 2 * wr;
+        const double *Ma = M + (wc * 32 + g4) + t4 * LDM;
+        const double *Mb = M + (wr * 64 + g4) + t4 * LDM;
+        if (d < 0) sym_update<0>(acc, Ma, Mb);
+        else if (d == 0) sym_update<1>(acc, Ma, Mb);
+        else if (d == 1) sym_update<2>(acc, Ma, Mb);
         __syncthreads();
     }
-
     CVXB_STAMP(1)
 #pragma unroll 1
     for (int t = 0; t < NB / PB; ++t) {
@@ -154,9 +175,11 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
 #undef CVXB_PUBLISH
         }
         __syncthreads();
-        // 2. 8x8 Cholesky of the diagonal block, redundantly in every warp.
-        //    lane -> row i = lane&7, columns 2g, 2g+1 with g = lane>>3
-        {
+        // 2. 8x8 Cholesky of the diagonal block by warp 0 alone (doing it redundantly in all
+        //    warps oversubscribes the shuffle unit: 24 SHFL per pivot per warp); warps 1-3 pick
+        //    the factor up from shared memory behind a 128-thread named barrier, warps 4-7 skip
+        //    to the CTA barrier.   lane -> row i = lane&7, columns 2g, 2g+1 with g = lane>>3
+        if (warp == 0) {
             const int i = lane & 7, g = lane >> 3;
             double d0 = P[(c0 + i) * SP + 2 * g], d1 = P[(c0 + i) * SP + 2 * g + 1];
             double rdiag = 0.0;    // lane j keeps 1/l_jj
@@ -182,17 +205,14 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
                 if (2 * g > j) d0 -= lij * lk0;
                 if (2 * g + 1 > j) d1 -= lij * lk1;
             }
-            if (warp < 4) {
-                double *D = Dw + warp * 80;
-                D[i * 8 + 2 * g] = d0;
-                D[i * 8 + 2 * g + 1] = d1;
-                if (lane < 8) D[64 + lane] = rdiag;
-            }
-            __syncwarp();
+            Dw[i * 8 + 2 * g] = d0;
+            Dw[i * 8 + 2 * g + 1] = d1;
+            if (lane < 8) Dw[64 + lane] = rdiag;
         }
+        if (warp < 4) asm volatile("bar.sync 1, 128;" ::: "memory");
         // 3. substitution on the rows below (one row per thread), zero rows above
         if (warp < 4) {
-            const double *D = Dw + warp * 80;
+            const double *D = Dw;
             const int r = warp * 32 + lane;
             double x[PB];
             if (r >= c0 + PB) {
@@ -216,8 +236,10 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
             for (int j = 0; j < PB; ++j) P[r * SP + j] = x[j];
         }
         __syncthreads();
-        // 4. rank-8 update of the fragments right/below the block: C -= P P'
-        {
+        // 4. rank-8 update of the fragments right/below the block: C -= P P'.  Skipping is
+        //    warp-uniform and coarse (whole warp / whole column fragment): per-tile tests put a
+        //    branch in front of every DMMA and cost more than the few dead tiles they save.
+        if (wr * 8 + 7 > t && wc * 4 + 3 > t) {
             double a[4][2], bfr[8][2];
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
@@ -231,7 +253,6 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
                 if (wc * 4 + cf <= t) continue;            // column block already final
 #pragma unroll
                 for (int rf = 0; rf < 8; ++rf) {
-                    if (wr * 8 + rf <= t) continue;        // rows at/above the diagonal block
                     dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf][0], bfr[rf][0]);
                     dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf][1], bfr[rf][1]);
                 }
