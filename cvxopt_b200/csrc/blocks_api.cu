@@ -229,16 +229,4 @@ int cvxb_symm(double *x, int n, int space) {
     return 0;
 }
 
-#define CVXB_NOT_YET(name)                                                           \
-    set_error(name ": not built yet in this round (O(cdim) IPM-side cone algebra)"); \
-    return CVXB_E_UNSUP
-
-int cvxb_scale2(const double *, double *, const cvxb_dims *, int, int) { CVXB_NOT_YET("scale2"); }
-int cvxb_sprod(double *, const double *, const cvxb_dims *, int, int) { CVXB_NOT_YET("sprod"); }
-int cvxb_sinv(double *, const double *, const cvxb_dims *, int) { CVXB_NOT_YET("sinv"); }
-int cvxb_trisc(double *, const cvxb_dims *, int) { CVXB_NOT_YET("trisc"); }
-int cvxb_triusc(double *, const cvxb_dims *, int) { CVXB_NOT_YET("triusc"); }
-int cvxb_sdot(const double *, const double *, const cvxb_dims *, double *, int) { CVXB_NOT_YET("sdot"); }
-int cvxb_max_step(double *, const cvxb_dims *, double *, double *, int) { CVXB_NOT_YET("max_step"); }
-
 }  // extern "C"

@@ -90,19 +90,74 @@ def symm(x, n, offset=0):
     _lib.check(lib.cvxb_symm(a.ctypes.data, n, _lib.HOST), "symm")
 
 
-def _not_yet(name):
-    def f(*a, **k):
-        raise NotImplementedError(
-            "cvxopt_b200.misc_solvers.%s: O(cdim) IPM-side cone algebra stays on the host in this "
-            "round (use cvxopt.misc_solvers.%s)" % (name, name))
-    f.__name__ = name
-    return f
+def _nlam(dims, mnl):
+    return mnl + int(dims["l"]) + sum(int(k) for k in dims["q"]) + sum(int(k) for k in dims["s"])
 
 
-scale2 = _not_yet("scale2")
-sprod = _not_yet("sprod")
-sinv = _not_yet("sinv")
-trisc = _not_yet("trisc")
-triusc = _not_yet("triusc")
-sdot = _not_yet("sdot")
-max_step = _not_yet("max_step")
+def _vec(x, n, name, offset=0):
+    a = _buf(x, name).reshape(-1, order="F")[offset:offset + n]
+    if a.size != n:
+        raise ValueError("%s: buffer too short" % name)
+    return a
+
+
+def scale2(lmbda, x, dims, mnl=0, inverse="N"):
+    """x := H(lambda^{1/2}) x or its inverse.  misc_solvers.c:256-401"""
+    lib = _lib.load()
+    cd, keep, cdim, _ = make_dims(dims, mnl)
+    la, xa = _vec(lmbda, _nlam(dims, mnl), "lmbda"), _vec(x, cdim, "x")
+    _lib.check(lib.cvxb_scale2(la.ctypes.data, xa.ctypes.data, C.byref(cd), ord(inverse), _lib.HOST), "scale2")
+
+
+def sprod(x, y, dims, mnl=0, diag="N"):
+    """x := y o x.  misc_solvers.c:634-767"""
+    lib = _lib.load()
+    cd, keep, cdim, _ = make_dims(dims, mnl)
+    xa = _vec(x, cdim, "x")
+    ya = _vec(y, _nlam(dims, mnl) if diag == "D" else cdim, "y")
+    _lib.check(lib.cvxb_sprod(xa.ctypes.data, ya.ctypes.data, C.byref(cd), ord(diag), _lib.HOST), "sprod")
+
+
+def sinv(x, y, dims, mnl=0):
+    """x := y o\\ x ('s' components of y diagonal).  misc_solvers.c:775-878"""
+    lib = _lib.load()
+    cd, keep, cdim, _ = make_dims(dims, mnl)
+    xa, ya = _vec(x, cdim, "x"), _vec(y, _nlam(dims, mnl), "y")
+    _lib.check(lib.cvxb_sinv(xa.ctypes.data, ya.ctypes.data, C.byref(cd), _lib.HOST), "sinv")
+
+
+def trisc(x, dims, offset=0):
+    """misc_solvers.c:887-935"""
+    lib = _lib.load()
+    cd, keep, cdim, _ = make_dims(dims, 0)
+    xa = _vec(x, cdim, "x", offset)
+    _lib.check(lib.cvxb_trisc(xa.ctypes.data, C.byref(cd), _lib.HOST), "trisc")
+
+
+def triusc(x, dims, offset=0):
+    """misc_solvers.c:940-986"""
+    lib = _lib.load()
+    cd, keep, cdim, _ = make_dims(dims, 0)
+    xa = _vec(x, cdim, "x", offset)
+    _lib.check(lib.cvxb_triusc(xa.ctypes.data, C.byref(cd), _lib.HOST), "triusc")
+
+
+def sdot(x, y, dims, mnl=0):
+    """misc_solvers.c:991-1039"""
+    lib = _lib.load()
+    cd, keep, cdim, _ = make_dims(dims, mnl)
+    xa, ya = _vec(x, cdim, "x"), _vec(y, cdim, "y")
+    out = C.c_double()
+    _lib.check(lib.cvxb_sdot(xa.ctypes.data, ya.ctypes.data, C.byref(cd), C.byref(out), _lib.HOST), "sdot")
+    return out.value
+
+
+def max_step(x, dims, mnl=0, sigma=None):
+    """min {t | x + t*e >= 0}.  misc_solvers.c:1052-1153.  's' blocks (eigenvalues) are not built
+    on the device yet: NotImplementedError, use cvxopt.misc_solvers.max_step for those."""
+    lib = _lib.load()
+    cd, keep, cdim, _ = make_dims(dims, mnl)
+    xa = _vec(x, cdim, "x")
+    out = C.c_double()
+    _lib.check(lib.cvxb_max_step(xa.ctypes.data, C.byref(cd), None, C.byref(out), _lib.HOST), "max_step")
+    return out.value

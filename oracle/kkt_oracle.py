@@ -293,3 +293,153 @@ class KktChol:
             x[:] = sla.solve_triangular(self.L, x, lower=True, trans="T")   # :1555
         bzp = self.Gs @ x - bzp                                      # :1344
         unpack(bzp, z, self.dims, self.mnl)                          # :1345
+
+
+# --------------------------------------------------------------------------- IPM-side cone algebra
+def _nlq(dims, mnl=0):
+    return mnl + dims["l"] + sum(dims["q"])
+
+
+def scale2(lmbda, x, dims, mnl=0, inverse="N"):
+    """misc_solvers.c:256-401 (python twin misc.py:170-247)."""
+    m = mnl + dims["l"]
+    if inverse == "N":
+        x[:m] /= lmbda[:m]
+    else:
+        x[:m] *= lmbda[:m]
+    for mk in dims["q"]:
+        nrm = np.linalg.norm(lmbda[m + 1:m + mk])
+        a = math.sqrt(lmbda[m] + nrm) * math.sqrt(lmbda[m] - nrm)
+        if inverse == "N":
+            lx = (lmbda[m] * x[m] - float(np.dot(lmbda[m + 1:m + mk], x[m + 1:m + mk]))) / a
+        else:
+            lx = float(np.dot(lmbda[m:m + mk], x[m:m + mk])) / a
+        x0 = x[m]
+        x[m] = lx
+        b = (x0 + lx) / (lmbda[m] / a + 1.0) / a
+        if inverse == "N":
+            b *= -1.0
+        x[m + 1:m + mk] += b * lmbda[m + 1:m + mk]
+        x[m:m + mk] *= (1.0 / a) if inverse == "N" else a
+        m += mk
+    ind2 = m
+    for mk in dims["s"]:
+        sql = np.sqrt(lmbda[ind2:ind2 + mk])
+        for j in range(mk):
+            c = sql * math.sqrt(lmbda[ind2 + j])
+            if inverse == "N":
+                x[m + j * mk:m + (j + 1) * mk] /= c
+            else:
+                x[m + j * mk:m + (j + 1) * mk] *= c
+        m += mk * mk
+        ind2 += mk
+    return x
+
+
+def sprod(x, y, dims, mnl=0, diag="N"):
+    """x := y o x.  misc_solvers.c:634-767"""
+    ind = mnl + dims["l"]
+    x[:ind] *= y[:ind]
+    for mk in dims["q"]:
+        a = float(np.dot(y[ind:ind + mk], x[ind:ind + mk]))
+        x0 = x[ind]
+        x[ind + 1:ind + mk] = y[ind] * x[ind + 1:ind + mk] + x0 * y[ind + 1:ind + mk]
+        x[ind] = a
+        ind += mk
+    if diag == "N":
+        for mk in dims["s"]:
+            A = _symL(x[ind:ind + mk * mk], mk)
+            Y = _symL(y[ind:ind + mk * mk], mk)
+            R = 0.5 * (A @ Y + Y @ A)
+            X = x[ind:ind + mk * mk].reshape(mk, mk, order="F")
+            il = np.tril_indices(mk)
+            X[il] = R[il]
+            x[ind:ind + mk * mk] = X.reshape(-1, order="F")
+            ind += mk * mk
+    else:
+        ind2 = ind
+        for mk in dims["s"]:
+            yk = y[ind2:ind2 + mk]
+            for k in range(mk):
+                x[ind + k * (mk + 1): ind + k * (mk + 1) + mk - k] *= 0.5 * (yk[k:] + yk[k])
+            ind += mk * mk
+            ind2 += mk
+    return x
+
+
+def sinv(x, y, dims, mnl=0):
+    """x := y o\\ x.  misc_solvers.c:775-878"""
+    ind = mnl + dims["l"]
+    x[:ind] /= y[:ind]
+    for mk in dims["q"]:
+        nrm = np.linalg.norm(y[ind + 1:ind + mk])
+        a = (y[ind] + nrm) * (y[ind] - nrm)
+        c = x[ind]
+        d = float(np.dot(x[ind + 1:ind + mk], y[ind + 1:ind + mk]))
+        x[ind] = c * y[ind] - d
+        x[ind + 1:ind + mk] *= a / y[ind]
+        x[ind + 1:ind + mk] += (d / y[ind] - c) * y[ind + 1:ind + mk]
+        x[ind:ind + mk] *= 1.0 / a
+        ind += mk
+    ind2 = ind
+    for mk in dims["s"]:
+        yk = y[ind2:ind2 + mk]
+        for k in range(mk):
+            x[ind + k * (mk + 1): ind + k * (mk + 1) + mk - k] /= 0.5 * (yk[k:] + yk[k])
+        ind += mk * mk
+        ind2 += mk
+    return x
+
+
+def trisc(x, dims, offset=0):
+    """misc_solvers.c:887-935"""
+    ox = offset + dims["l"] + sum(dims["q"])
+    for nk in dims["s"]:
+        X = x[ox:ox + nk * nk].reshape(nk, nk, order="F")
+        X[np.triu_indices(nk, 1)] = 0.0
+        X[np.tril_indices(nk, -1)] *= 2.0
+        x[ox:ox + nk * nk] = X.reshape(-1, order="F")
+        ox += nk * nk
+    return x
+
+
+def triusc(x, dims, offset=0):
+    """misc_solvers.c:940-986"""
+    ox = offset + dims["l"] + sum(dims["q"])
+    for nk in dims["s"]:
+        X = x[ox:ox + nk * nk].reshape(nk, nk, order="F")
+        X[np.tril_indices(nk, -1)] *= 0.5
+        x[ox:ox + nk * nk] = X.reshape(-1, order="F")
+        ox += nk * nk
+    return x
+
+
+def sdot(x, y, dims, mnl=0):
+    """misc_solvers.c:991-1039"""
+    m = _nlq(dims, mnl)
+    a = float(np.dot(x[:m], y[:m]))
+    for nk in dims["s"]:
+        X = x[m:m + nk * nk].reshape(nk, nk, order="F")
+        Y = y[m:m + nk * nk].reshape(nk, nk, order="F")
+        a += float(np.dot(np.diag(X), np.diag(Y)))
+        il = np.tril_indices(nk, -1)
+        a += 2.0 * float(np.dot(X[il], Y[il]))
+        m += nk * nk
+    return a
+
+
+def max_step(x, dims, mnl=0):
+    """min {t | x + t e >= 0}, misc_solvers.c:1052-1153 (without the sigma output)."""
+    ind = mnl + dims["l"]
+    t = -np.finfo(np.float32).max
+    if ind:
+        t = max(t, float(np.max(-x[:ind])))
+    for mk in dims["q"]:
+        t = max(t, float(np.linalg.norm(x[ind + 1:ind + mk]) - x[ind]))
+        ind += mk
+    for mk in dims["s"]:
+        if mk:
+            w = np.linalg.eigvalsh(_symL(x[ind:ind + mk * mk], mk))
+            t = max(t, -float(w[0]))
+        ind += mk * mk
+    return t if ind else 0.0

@@ -222,3 +222,43 @@ def test_misc_solvers_mirror(dims):
     ms.symm(S, 7)
     ko.symm(So, 7)
     assert np.array_equal(S, So)
+
+
+@pytest.mark.parametrize("dims", [{"l": 6, "q": [4, 9, 1], "s": []}, {"l": 5, "q": [7], "s": [3, 8]}, {"l": 0, "q": [], "s": [20]}])
+def test_misc_solvers_mirror_ipm_side(dims):
+    """scale2 / sprod / sinv / sdot / max_step / trisc / triusc on the device vs the oracle."""
+    from cvxopt_b200 import misc_solvers as ms
+    from problems import cone_point
+    rng = np.random.Generator(np.random.PCG64(15))
+    K = cone_dim(dims)
+    W, lm = random_scaling(dims, seed=9)
+    mask = np.ones(K, bool)
+    off = dims["l"] + sum(dims["q"])
+    for k in dims["s"]:
+        M = np.ones((k, k), bool); M[np.triu_indices(k, 1)] = False
+        mask[off:off + k * k] = M.reshape(-1, order="F"); off += k * k
+    for inv in "NI":
+        x = cone_point(dims, rng); xo = x.copy()
+        ms.scale2(lm, x, dims, inverse=inv); ko.scale2(lm, xo, dims, inverse=inv)
+        assert relerr(x, xo) < 1e-13
+    x, y = cone_point(dims, rng), cone_point(dims, rng); xo = x.copy()
+    ms.sprod(x, y, dims); ko.sprod(xo, y, dims)
+    assert relerr(x[mask], xo[mask]) < 1e-13
+    x = cone_point(dims, rng); xo = x.copy()
+    ms.sprod(x, lm, dims, diag="D"); ko.sprod(xo, lm, dims, diag="D")
+    assert relerr(x[mask], xo[mask]) < 1e-13
+    x = cone_point(dims, rng); xo = x.copy()
+    ms.sinv(x, lm, dims); ko.sinv(xo, lm, dims)
+    assert relerr(x[mask], xo[mask]) < 1e-13
+    x, y = cone_point(dims, rng), cone_point(dims, rng)
+    assert abs(ms.sdot(x, y, dims) - ko.sdot(x, y, dims)) <= 1e-12 * abs(ko.sdot(x, y, dims))
+    for f, fo in ((ms.trisc, ko.trisc), (ms.triusc, ko.triusc)):
+        x = rng.standard_normal(K); xo = x.copy()
+        f(x, dims); fo(xo, dims)
+        assert np.array_equal(x, xo)
+    x = rng.standard_normal(K)
+    if dims["s"]:
+        with pytest.raises(NotImplementedError):
+            ms.max_step(x, dims)
+    else:
+        assert abs(ms.max_step(x, dims) - ko.max_step(x, dims)) < 1e-13

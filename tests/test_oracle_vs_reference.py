@@ -136,6 +136,52 @@ def test_kkt_chol_with_equalities_matches_reference(ref, dims, with_H):
     np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-11)
 
 
+@pytest.mark.parametrize("dims", DIMS)
+def test_ipm_side_cone_algebra_matches_reference(ref, dims):
+    """scale2 / sprod / sinv / sdot / max_step / trisc / triusc restatements vs misc_solvers."""
+    from cvxopt import misc
+    rng = np.random.Generator(np.random.PCG64(41))
+    K = cone_dim(dims)
+    nl = dims["l"] + sum(dims["q"]) + sum(dims["s"])
+    W, lm = random_scaling(dims, seed=6)
+    m = ref.matrix
+    for inv in "NI":
+        x = cone_point(dims, rng)
+        xr = m(x)
+        ko.scale2(lm, x, dims, inverse=inv)
+        misc.scale2(m(lm), xr, dims, inverse=inv)
+        np.testing.assert_allclose(x, np.array(xr).ravel(), rtol=1e-12, atol=1e-13)
+    x, y = cone_point(dims, rng), cone_point(dims, rng)
+    xr, yr = m(x), m(y)
+    ko.sprod(x, y, dims)
+    misc.sprod(xr, yr, dims)
+    mask = np.ones(K, bool)
+    off = dims["l"] + sum(dims["q"])
+    for k in dims["s"]:
+        M = np.ones((k, k), bool); M[np.triu_indices(k, 1)] = False
+        mask[off:off + k * k] = M.reshape(-1, order="F"); off += k * k
+    np.testing.assert_allclose(x[mask], np.array(xr).ravel()[mask], rtol=1e-12, atol=1e-12)
+    for fn_o, fn_r in ((ko.sprod, misc.sprod), (ko.sinv, misc.sinv)):
+        x = cone_point(dims, rng)
+        xr = m(x)
+        if fn_o is ko.sprod:
+            fn_o(x, lm, dims, diag="D"); fn_r(xr, m(lm), dims, diag="D")
+        else:
+            fn_o(x, lm, dims); fn_r(xr, m(lm), dims)
+        np.testing.assert_allclose(x[mask], np.array(xr).ravel()[mask], rtol=1e-11, atol=1e-12)
+    x, y = cone_point(dims, rng), cone_point(dims, rng)
+    np.testing.assert_allclose(ko.sdot(x, y, dims), misc.sdot(m(x), m(y), dims), rtol=1e-13)
+    x = rng.standard_normal(K)
+    for k_off, k in zip(np.cumsum([dims["l"] + sum(dims["q"])] + [s * s for s in dims["s"]])[:-1], dims["s"]):
+        X = x[k_off:k_off + k * k].reshape(k, k, order="F"); X[:] = (X + X.T) / 2
+        x[k_off:k_off + k * k] = X.reshape(-1, order="F")
+    np.testing.assert_allclose(ko.max_step(x.copy(), dims), misc.max_step(m(x), dims), rtol=1e-10, atol=1e-12)
+    for fo, fr in ((ko.trisc, misc.trisc), (ko.triusc, misc.triusc)):
+        x = rng.standard_normal(K); xr = m(x)
+        fo(x, dims); fr(xr, dims)
+        assert np.array_equal(x, np.array(xr).ravel())
+
+
 def test_reference_known_answer_coneqp(ref):
     """reference tests/test_examples.py:27-29 (examples/doc/chap8/coneqp.py): the only
     reference test whose numbers flow through kkt_chol."""
