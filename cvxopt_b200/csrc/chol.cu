@@ -373,7 +373,7 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
 // flag -> 128x128 smem GEMV -> 128x128 register GEMV -> flag.
 constexpr int TR_CH = 32;                       // columns per ring chunk
 constexpr int TR_R = 5;                         // ring depth
-constexpr int TRSV_SMEM = (TR_R * NB * TR_CH + 4 * NB) * 8;
+constexpr int TRSV_SMEM = (TR_R * NB * TR_CH + 4 * NB + 32 * 129) * 8;
 
 template <bool TRANS, bool VEC>
 __global__ void __launch_bounds__(256, 1)
@@ -390,6 +390,7 @@ trsv_kernel(int n, const double *__restrict__ L, long long ldl, const double *__
     double *xs = ring + TR_R * NB * TR_CH;      // 128
     double *part = xs + NB;                     // 2 x 128
     double *tvec = part + 2 * NB;               // 128
+    double *part2 = tvec + NB;                  // 32 x 129: per-lane column partials (backward)
     const int nblk = (n + NB - 1) / NB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bi = TRANS ? (nblk - 1 - (int)blockIdx.x) : (int)blockIdx.x;
@@ -405,6 +406,8 @@ trsv_kernel(int n, const double *__restrict__ L, long long ldl, const double *__
         for (int k = 0; k < 64; ++k) ireg[k] = ip[k * NB];
     }
 
+    // this block's right-hand side is input data nobody else writes: fetch it before the chain
+    const double bown = (tid < ni) ? b[i0 + tid] : 0.0;
     const int nb_dep = TRANS ? (nblk - 1 - bi) : bi;         // blocks this CTA depends on
     const int nchunks = nb_dep * (NB / TR_CH);
     // chunk q -> (block j, column chunk cc)
@@ -484,14 +487,22 @@ trsv_kernel(int n, const double *__restrict__ L, long long ldl, const double *__
     if (!TRANS) {
         part[half * NB + r] = acc;
         __syncthreads();
-        if (tid < NB) tvec[tid] = (tid < ni) ? (b[i0 + tid] - part[tid] - part[NB + tid]) : 0.0;
+        if (tid < NB) tvec[tid] = (tid < ni) ? (bown - part[tid] - part[NB + tid]) : 0.0;
         __syncthreads();
     } else {
+        // cross-lane reduction of the 16 column partials through shared memory (16 warp-shuffle
+        // trees cost ~1.6 us on the critical path of every block step)
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const double a = warp_sum(accc[q]);
             const int c = (q >> 2) * TR_CH + warp * 4 + (q & 3);
-            if (lane == 0) tvec[c] = (c < ni) ? (b[i0 + c] - a) : 0.0;
+            part2[lane * 129 + c] = accc[q];
+        }
+        __syncthreads();
+        if (tid < NB) {
+            double sacc = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) sacc += part2[l * 129 + tid];
+            tvec[tid] = (tid < ni) ? (bown - sacc) : 0.0;
         }
         __syncthreads();
     }
