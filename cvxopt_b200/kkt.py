@@ -43,6 +43,8 @@ def _vec_inplace(a, n, name):
     arr = np.asarray(a)
     if arr.dtype != np.float64 or arr.size != n:
         raise TypeError("%s must be a 'd' matrix of size (%d,1)" % (name, n))
+    if n == 0:
+        return np.zeros(1)          # nothing to read or write; keep a valid pointer
     flat = arr.reshape(-1, order="F") if arr.ndim > 1 else arr
     if not np.shares_memory(flat, arr) or not flat.flags.writeable or not flat.flags.c_contiguous:
         raise TypeError("%s must be a contiguous writable buffer" % name)

@@ -262,3 +262,31 @@ def test_misc_solvers_mirror_ipm_side(dims):
             ms.max_step(x, dims)
     else:
         assert abs(ms.max_step(x, dims) - ko.max_step(x, dims)) < 1e-13
+
+
+def test_no_cone_rows_and_handle_lifecycle():
+    """cdim == 0 (unconstrained QP step: K = H) and repeated create/destroy (no leaks, no stale state)."""
+    import torch
+    import cvxopt_b200
+    n = 70
+    rng = np.random.Generator(np.random.PCG64(2))
+    B = rng.standard_normal((n, n))
+    H = np.asfortranarray(B @ B.T + np.eye(n))
+    dims = {"l": 0, "q": [], "s": []}
+    W = {"d": np.zeros(0), "di": np.zeros(0), "v": [], "beta": [], "r": [], "rti": []}
+    fac = cvxopt_b200.kkt_chol(np.zeros((0, n), order="F"), dims)
+    solve = fac(W, H)
+    x = rng.standard_normal(n)
+    x0 = x.copy()
+    solve(x, None, np.zeros(0))
+    assert relerr(x, np.linalg.solve(H, x0)) < 1e-11
+    fac.close()
+    free0 = torch.cuda.mem_get_info()[0]
+    G = np.asfortranarray(rng.standard_normal((900, 300)))
+    Wl, _ = random_scaling({"l": 900, "q": [], "s": []}, 3)
+    for _ in range(20):
+        f = cvxopt_b200.kkt_chol(G, {"l": 900, "q": [], "s": []})
+        f(Wl)
+        f.close()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 << 20, (free0, free1)
