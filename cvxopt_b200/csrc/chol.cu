@@ -627,15 +627,22 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
         count_launch();
         CVXB_LAUNCH_CHECK();
         CVXB_CUDA(cudaEventRecord(w.ev_dg[jb], D));
-        if (jb > 0) {
-            // L(j:, j-1) back into A, now that the raw tile has been consumed
+        // L(j:, j-1) goes back into A once Dg(jb) has consumed the raw tile; the copy rides on the
+        // panel stream T behind this step's TRSM / column update (it used to sit on D, where its
+        // 3-5 us were part of the diagonal chain)
+        auto copy_back_prev = [&]() -> int {
+            if (jb == 0) return 0;
             const int jp = j - NB, mp = n - j;
-            CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_tr[jb - 1], 0));
             CVXB_CUDA(cudaMemcpy2DAsync(A + j + (long long)jp * lda, (size_t)lda * sizeof(double),
                                         w.panel[(jb - 1) & 1], (size_t)ldw * sizeof(double),
-                                        (size_t)mp * sizeof(double), NB, cudaMemcpyDeviceToDevice, D));
+                                        (size_t)mp * sizeof(double), NB, cudaMemcpyDeviceToDevice, T));
+            return 0;
+        };
+        if (m <= 0) {
+            CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_dg[jb], 0));
+            CVXB_TRY(copy_back_prev());
+            break;
         }
-        if (m <= 0) break;
         double *A21 = Ajj + wj;
         double *A22 = A21 + (long long)wj * lda;
         double *Wp = w.panel[jb & 1];
@@ -665,6 +672,7 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
             CVXB_TRY(dmma_gemm(c, T));
         }
         CVXB_CUDA(cudaEventRecord(w.ev_c0[jb], T));
+        CVXB_TRY(copy_back_prev());
         // ---- U: the rest of the trailing matrix ----
         if (m > NB) {
             CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_tr[jb], 0));
@@ -750,7 +758,6 @@ int potrf_lower_batched(int n, double *A, int lda, long long sA, double *inv, lo
                                                         nullptr, nullptr);
         count_launch();
         CVXB_LAUNCH_CHECK();
-        if (m <= 0) break;
         double *A21 = Ajj + wj;
         double *A22 = A21 + (long long)wj * lda;
         GemmDesc g;
