@@ -758,6 +758,7 @@ int potrf_lower_batched(int n, double *A, int lda, long long sA, double *inv, lo
                                                         nullptr, nullptr);
         count_launch();
         CVXB_LAUNCH_CHECK();
+        if (m <= 0) break;
         double *A21 = Ajj + wj;
         double *A22 = A21 + (long long)wj * lda;
         GemmDesc g;
