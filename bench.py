@@ -385,8 +385,9 @@ def main():
                          "peak_source": "measured DMMA.8x8x4 pipe rate on this pool (tools/fp64_peak.cu; "
                                         "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 = 35.4)",
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
-                         # committed capture profiles/r01d_syrk_n8192_ncu_summary.md (n=8192 only)
-                         "traffic": (11.05e9 + 0.27e9) if (n == 8192 and m == 16384) else None,
+                         # committed capture profiles/r01j_syrk_band_order_dram.md (n=8192 only; 11.3 GB
+                         # before the band-major tile order, profiles/r01d_syrk_n8192_ncu_summary.md)
+                         "traffic": (7.30e9 + 0.275e9) if (n == 8192 and m == 16384) else None,
                          "algorithmic_bytes": 8.0 * m * n + 8.0 * n * n},
         }
         if world == 1 and not args.no_cpu_baseline:
