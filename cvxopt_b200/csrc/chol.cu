@@ -175,39 +175,38 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
 #undef CVXB_PUBLISH
         }
         __syncthreads();
-        // 2. 8x8 Cholesky of the diagonal block by warp 0 alone (doing it redundantly in all
-        //    warps oversubscribes the shuffle unit: 24 SHFL per pivot per warp); warps 1-3 pick
-        //    the factor up from shared memory behind a 128-thread named barrier, warps 4-7 skip
-        //    to the CTA barrier.   lane -> row i = lane&7, columns 2g, 2g+1 with g = lane>>3
-        if (warp == 0) {
-            const int i = lane & 7, g = lane >> 3;
-            double d0 = P[(c0 + i) * SP + 2 * g], d1 = P[(c0 + i) * SP + 2 * g + 1];
-            double rdiag = 0.0;    // lane j keeps 1/l_jj
+        // 2. 8x8 Cholesky of the diagonal block by a single lane; warps 0-3 pick the factor up from
+        //    shared memory behind a 128-thread named barrier, warps 4-7 skip to the CTA barrier.
+        if (warp == 0 && lane == 0) {
+            // one lane, 36 registers, no shuffles: the critical path per pivot is one rsqrt, one
+            // multiply and one FMA (the 32-lane shuffle version spent ~200 cycles per pivot)
+            double a[PB][PB];
+#pragma unroll
+            for (int i = 0; i < PB; ++i)
+#pragma unroll
+                for (int k = 0; k <= i; ++k) a[i][k] = P[(c0 + i) * SP + k];
             bool bad = false;
 #pragma unroll
             for (int j = 0; j < PB; ++j) {
-                const int gj = j >> 1;
-                const double colv = (j & 1) ? d1 : d0;            // column j lives in group gj
-                const double piv = __shfl_sync(0xffffffffu, colv, j + 8 * gj);
-                if (!(piv > 0.0)) {
-                    if (!bad && tid == 0) atomicCAS(info, 0, joff + c0 + j + 1);
+                const double piv = a[j][j];
+                if (!(piv > 0.0) && !bad) {
+                    atomicCAS(info, 0, joff + c0 + j + 1);
                     bad = true;
                 }
-                const double rs = rsqrt(piv), s = piv * rs;      // one long-latency op per pivot
-                if (lane == j) rdiag = rs;
-                double lij = __shfl_sync(0xffffffffu, colv, i + 8 * gj) * rs;
-                const double lk0 = __shfl_sync(0xffffffffu, colv, 2 * g + 8 * gj) * rs;
-                const double lk1 = __shfl_sync(0xffffffffu, colv, 2 * g + 1 + 8 * gj) * rs;
-                if (i == j) lij = s;
-                if (g == gj) {                                    // final column j
-                    if (j & 1) d1 = lij; else d0 = lij;
-                }
-                if (2 * g > j) d0 -= lij * lk0;
-                if (2 * g + 1 > j) d1 -= lij * lk1;
+                const double rs = rsqrt(piv);
+                a[j][j] = piv * rs;
+                Dw[64 + j] = rs;
+#pragma unroll
+                for (int i = j + 1; i < PB; ++i) a[i][j] *= rs;
+#pragma unroll
+                for (int k = j + 1; k < PB; ++k)
+#pragma unroll
+                    for (int i = k; i < PB; ++i) a[i][k] -= a[i][j] * a[k][j];
             }
-            Dw[i * 8 + 2 * g] = d0;
-            Dw[i * 8 + 2 * g + 1] = d1;
-            if (lane < 8) Dw[64 + lane] = rdiag;
+#pragma unroll
+            for (int i = 0; i < PB; ++i)
+#pragma unroll
+                for (int k = 0; k < PB; ++k) Dw[i * 8 + k] = (k <= i) ? a[i][k] : 0.0;
         }
         if (warp < 4) asm volatile("bar.sync 1, 128;" ::: "memory");
         // 3. substitution on the rows below (one row per thread), zero rows above
