@@ -123,6 +123,13 @@ struct CholWork {
     cudaEvent_t ev_end_t = nullptr;
     std::vector<cudaEvent_t> ev_dg, ev_tr, ev_c0, ev_r;   // one per block step
     unsigned long long *trace = nullptr;  // CVXB_TRACE=1: per step {Dg, Tr, C0, R} x {start, end}
+    struct GraphEntry {                    // captured factorisation, keyed by its arguments
+        int n = 0, lda = 0, launches = 0;
+        const void *A = nullptr, *inv = nullptr;
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<GraphEntry> graphs;
+    bool graph_failed = false;
     int r_valid[2] = {-1, -1};            // which steps recorded ev_r (steps without bulk work do not)
     cudaEvent_t ev_start = nullptr, ev_panel = nullptr, ev_rest = nullptr, ev_end_p = nullptr,
                 ev_end_u = nullptr;
