@@ -1,10 +1,15 @@
 // The O(cdim) cone algebra of the IPM side, mirror of src/C/misc_solvers.c:
 //   scale2 (:256-401), sprod (:634-767), sinv (:775-878), trisc (:887-935), triusc (:940-986),
-//   sdot (:991-1039), max_step (:1052-1153; 'l' and 'q' cones — the 's' part needs a symmetric
-//   eigensolver and returns CVXB_E_UNSUP).
+//   sdot (:991-1039), max_step (:1052-1153).
 // One CTA walks the whole cone vector; reductions inside a 'q' cone / for sdot are block-wide.
+// The 's' part of max_step (reference: dsyevr_ for the smallest eigenvalue, dsyevd_ when sigma is
+// given, :1099-1150) is a parallel-order cyclic Jacobi eigensolver: every round applies N/2 disjoint
+// plane rotations at once, one thread per 2x2 block of J'AJ, ping-ponging between two copies so a
+// round is a single race-free pass.
 #include "cone.cuh"
 #include <map>
+#include <vector>
+#include <algorithm>
 #include <cfloat>
 
 using namespace cvxb;
@@ -190,6 +195,211 @@ __global__ void max_step_kernel(const double *x, Cones c, double *out) {
     if (tid == 0) *out = (m > 0) ? t : 0.0;
 }
 
+
+// ---- symmetric eigensolver for the 's' blocks (parallel-order cyclic Jacobi) ----------------
+// Round r of the round-robin ("chess tournament") ordering on N (even) indices: N/2 disjoint pairs.
+__device__ __forceinline__ void rr_pair(int N, int r, int k, int &p, int &q) {
+    int a, b;
+    if (k == 0) { a = N - 1; b = r; }
+    else { a = (r + k) % (N - 1); b = (r - k + (N - 1)) % (N - 1); }
+    p = min(a, b); q = max(a, b);
+}
+
+// rotation J = [c s; -s c] annihilating a_pq in J'[app apq; apq aqq]J;  t = tan of the angle
+__device__ __forceinline__ void jac_rot(double app, double aqq, double apq, double &c, double &s, double &t) {
+    if (apq == 0.0) { c = 1.0; s = 0.0; t = 0.0; return; }
+    const double tau = (aqq - app) / (2.0 * apq);
+    t = copysign(1.0, tau) / (fabs(tau) + sqrt(1.0 + tau * tau));     // tau*tau = inf -> t = 0
+    c = 1.0 / sqrt(1.0 + t * t);
+    s = t * c;
+}
+
+// One thread's share of a round: the 2x2 block (rows of pair I, columns of pair J) of
+// dst = J'.src.J, and the same block of V := V.J.  Indices >= mk belong to the padding.
+template <bool WITH_V>
+__device__ __forceinline__ void jac_block(const double *src, double *dst, double *V, int mk, int N,
+                                          int r, int I, int J) {
+    int pi, qi, pj, qj;
+    rr_pair(N, r, I, pi, qi);
+    rr_pair(N, r, J, pj, qj);
+    if (pi >= mk || pj >= mk) return;
+    const bool vi = qi < mk, vj = qj < mk;
+    double ci = 1, si = 0, ti = 0, cj = 1, sj = 0, tj = 0;
+    if (vi) jac_rot(src[pi + (size_t)pi * mk], src[qi + (size_t)qi * mk], src[qi + (size_t)pi * mk], ci, si, ti);
+    if (I == J) { cj = ci; sj = si; tj = ti; }
+    else if (vj) jac_rot(src[pj + (size_t)pj * mk], src[qj + (size_t)qj * mk], src[qj + (size_t)pj * mk], cj, sj, tj);
+    const double b00 = src[pi + (size_t)pj * mk];
+    const double b01 = vj ? src[pi + (size_t)qj * mk] : 0.0;
+    const double b10 = vi ? src[qi + (size_t)pj * mk] : 0.0;
+    const double b11 = (vi && vj) ? src[qi + (size_t)qj * mk] : 0.0;
+    double d00, d01, d10, d11;
+    if (I == J) {
+        d00 = b00 - ti * b10; d11 = b11 + ti * b10; d01 = 0.0; d10 = 0.0;
+    } else {
+        const double r00 = ci * b00 - si * b10, r01 = ci * b01 - si * b11;
+        const double r10 = si * b00 + ci * b10, r11 = si * b01 + ci * b11;
+        d00 = cj * r00 - sj * r01; d01 = sj * r00 + cj * r01;
+        d10 = cj * r10 - sj * r11; d11 = sj * r10 + cj * r11;
+    }
+    dst[pi + (size_t)pj * mk] = d00;
+    if (vj) dst[pi + (size_t)qj * mk] = d01;
+    if (vi) dst[qi + (size_t)pj * mk] = d10;
+    if (vi && vj) dst[qi + (size_t)qj * mk] = d11;
+    if (WITH_V) {
+        const double v00 = V[pi + (size_t)pj * mk];
+        const double v01 = vj ? V[pi + (size_t)qj * mk] : 0.0;
+        V[pi + (size_t)pj * mk] = cj * v00 - sj * v01;
+        if (vj) V[pi + (size_t)qj * mk] = sj * v00 + cj * v01;
+        if (vi) {
+            const double v10 = V[qi + (size_t)pj * mk];
+            const double v11 = vj ? V[qi + (size_t)qj * mk] : 0.0;
+            V[qi + (size_t)pj * mk] = cj * v10 - sj * v11;
+            if (vj) V[qi + (size_t)qj * mk] = sj * v10 + cj * v11;
+        }
+    }
+}
+
+struct JacArgs {
+    const double *x;        // first 's' row of the cone vector (lower triangles significant)
+    double *w0, *w1, *V;    // three work copies, each sum(mk^2), same block offsets as x
+    const int *s, *soff, *sigoff;
+    double *sigma;          // sum(mk): eigenvalues, ascending inside each block
+    double *xout;           // eigenvectors -> 's' blocks of x (nullptr: eigenvalues only)
+    double *stats;          // 2 per block: off-diagonal and total squared Frobenius norms
+    int *perm;              // sum(mk): rank of each unsorted eigenvalue
+    int N;                  // padded (even) order shared by all blocks of the launch
+};
+
+__global__ void jac_init_kernel(JacArgs a) {
+    const int k = blockIdx.y, mk = a.s[k];
+    const size_t o = a.soff[k];
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)mk * mk; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % mk), j = (int)(e / mk);
+        a.w0[o + e] = (i >= j) ? a.x[o + e] : a.x[o + j + (size_t)i * mk];
+        if (a.V) a.V[o + e] = (i == j) ? 1.0 : 0.0;
+    }
+}
+
+template <bool WITH_V>
+__global__ void jac_round_kernel(JacArgs a, int r, int flip) {
+    const int k = blockIdx.z, mk = a.s[k];
+    const int I = blockIdx.y * blockDim.y + threadIdx.y, J = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= a.N / 2 || J >= a.N / 2) return;
+    const size_t o = a.soff[k];
+    jac_block<WITH_V>((flip ? a.w1 : a.w0) + o, (flip ? a.w0 : a.w1) + o, a.V + (WITH_V ? o : 0), mk, a.N, r, I, J);
+}
+
+__global__ void jac_off_kernel(JacArgs a, int flip) {
+    __shared__ double sh[32];
+    const int k = blockIdx.x, mk = a.s[k];
+    const double *S = (flip ? a.w1 : a.w0) + a.soff[k];
+    double off = 0, tot = 0;
+    for (size_t e = threadIdx.x; e < (size_t)mk * mk; e += blockDim.x) {
+        const double v = S[e] * S[e];
+        tot += v;
+        if (e % mk != e / mk) off += v;
+    }
+    off = blk_sum(off, sh); tot = blk_sum(tot, sh);
+    if (threadIdx.x == 0) { a.stats[2 * k] = off; a.stats[2 * k + 1] = tot; }
+}
+
+// eigenvalues = diagonal; rank them (stable), write sigma ascending
+__global__ void jac_sort_kernel(JacArgs a, int flip) {
+    const int k = blockIdx.x, mk = a.s[k];
+    const double *S = (flip ? a.w1 : a.w0) + a.soff[k];
+    for (int i = threadIdx.x; i < mk; i += blockDim.x) {
+        const double di = S[i + (size_t)i * mk];
+        int rank = 0;
+        for (int j = 0; j < mk; ++j) {
+            const double dj = S[j + (size_t)j * mk];
+            rank += (dj < di) || (dj == di && j < i);
+        }
+        a.sigma[a.sigoff[k] + rank] = di;
+        a.perm[a.sigoff[k] + i] = rank;
+    }
+}
+
+__global__ void jac_vec_kernel(JacArgs a) {
+    const int k = blockIdx.y, mk = a.s[k];
+    const size_t o = a.soff[k];
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)mk * mk; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % mk), j = (int)(e / mk);
+        a.xout[o + i + (size_t)a.perm[a.sigoff[k] + j] * mk] = a.V[o + e];
+    }
+}
+
+// convergence of one block from its (off^2, total^2): at rounding level, or stagnating just above it
+__host__ __device__ inline bool jac_done(double off2, double tot2, double prev_off2, int mk) {
+    const double eps = 2.220446049250313e-16;
+    if (!(off2 > eps * eps * (double)mk * tot2)) return off2 == off2;       // NaN never converges
+    return off2 <= 1e-26 * tot2 && off2 >= 0.25 * prev_off2;
+}
+
+// All blocks of order <= 64: one CTA per block runs every sweep itself (block-level barriers only).
+template <bool WITH_V>
+__global__ void __launch_bounds__(1024) jac_small_kernel(JacArgs a, int max_sweeps, int *fail) {
+    __shared__ double sh[32];
+    const int k = blockIdx.x, mk = a.s[k];
+    if (mk == 0) return;
+    const size_t o = a.soff[k];
+    double *w0 = a.w0 + o, *w1 = a.w1 + o, *V = WITH_V ? a.V + o : nullptr;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < mk * mk; e += nt) {
+        const int i = e % mk, j = e / mk;
+        w0[e] = (i >= j) ? a.x[o + e] : a.x[o + j + (size_t)i * mk];
+        if (WITH_V) V[e] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int N = max(2, mk + (mk & 1)), h = N / 2;
+    const int I = tid / h, J = tid % h;
+    double prev = 1e300;
+    int sweep = 0;
+    bool ok = false;
+    for (;; ++sweep) {
+        double off = 0, tot = 0;
+        for (int e = tid; e < mk * mk; e += nt) {
+            const double v = w0[e] * w0[e];
+            tot += v;
+            if (e % mk != e / mk) off += v;
+        }
+        off = blk_sum(off, sh); tot = blk_sum(tot, sh);
+        if (jac_done(off, tot, prev, mk)) { ok = true; break; }
+        if (sweep == max_sweeps) break;
+        prev = off;
+        for (int r = 0; r < N - 1; ++r) {
+            if (I < h) jac_block<WITH_V>(w0, w1, V, mk, N, r, I, J);
+            __syncthreads();
+            double *t = w0; w0 = w1; w1 = t;
+        }
+    }
+    if (!ok && tid == 0) atomicExch(fail, 1);
+    for (int i = tid; i < mk; i += nt) {
+        const double di = w0[i + (size_t)i * mk];
+        int rank = 0;
+        for (int j = 0; j < mk; ++j) {
+            const double dj = w0[j + (size_t)j * mk];
+            rank += (dj < di) || (dj == di && j < i);
+        }
+        a.sigma[a.sigoff[k] + rank] = di;
+        if (WITH_V) a.perm[a.sigoff[k] + i] = rank;
+    }
+    if (WITH_V) {
+        __syncthreads();
+        for (int e = tid; e < mk * mk; e += nt) {
+            const int i = e % mk, j = e / mk;
+            a.xout[o + i + (size_t)a.perm[a.sigoff[k] + j] * mk] = V[e];
+        }
+    }
+}
+
+// t := max(t, -lambda_min) over the 's' blocks (sigma ascending per block)
+__global__ void max_step_s_kernel(double *out, const double *sigma, const int *s, const int *sigoff,
+                                  int ns, int any_lq) {
+    double t = any_lq ? *out : -FLT_MAX;
+    for (int k = 0; k < ns; ++k) if (s[k] > 0) t = fmax(t, -sigma[sigoff[k]]);
+    *out = t;
+}
+
 struct VCtx { cudaStream_t st = nullptr; bool ok = false; };
 VCtx g_v;
 int vctx(cudaStream_t *st) {
@@ -342,27 +552,136 @@ int cvxb_sdot(const double *x, const double *y, const cvxb_dims *dims, double *r
     return 0;
 }
 
+// Eigen-decomposition of every 's' block of the device cone vector xs (first 's' row).
+// sigma_dev: sum(mk) eigenvalues (ascending per block); with_vectors: the blocks of xs are
+// overwritten by the eigenvectors (columns ordered like sigma), as dsyevd_ 'V' does in the reference.
+static int sym_eig_blocks(const ConeLayout &c, double *xs, double *sigma_dev, const int *d_sigoff,
+                          bool with_vectors, cudaStream_t st) {
+    const int MAX_SWEEPS = 40;
+    int sums = 0;
+    for (int v : c.s) sums += v;
+    if (c.maxs == 0) return 0;
+    const size_t m2 = (size_t)c.sums2;
+    double *work = nullptr, *stats = nullptr;
+    int *perm = nullptr, *fail = nullptr;
+    std::vector<double> hstats(2 * (size_t)c.ns), prev(c.ns, 1e300);
+    int rc = 0;
+    auto done = [&](int r) {
+        cudaStreamSynchronize(st);
+        cudaFree(work); cudaFree(stats); cudaFree(perm); cudaFree(fail);
+        return r;
+    };
+    if (cudaMalloc(&work, (with_vectors ? 3 : 2) * m2 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&stats, 2 * (size_t)c.ns * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&perm, (size_t)(sums ? sums : 1) * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&fail, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("max_step: out of device memory for the eigensolver workspace");
+        return done(CVXB_E_NOMEM);
+    }
+    JacArgs a;
+    a.x = xs; a.w0 = work; a.w1 = work + m2; a.V = with_vectors ? work + 2 * m2 : nullptr;
+    a.s = c.d_s; a.soff = c.d_soff; a.sigoff = d_sigoff;
+    a.sigma = sigma_dev; a.xout = with_vectors ? xs : nullptr; a.stats = stats; a.perm = perm;
+    a.N = std::max(2, c.maxs + (c.maxs & 1));
+    const int h = a.N / 2;
+    if (c.maxs <= 64) {
+        if (cudaMemsetAsync(fail, 0, sizeof(int), st) != cudaSuccess) return done(CVXB_E_CUDA);
+        const int nt = std::max(32, (h * h + 31) / 32 * 32);
+        if (with_vectors) jac_small_kernel<true><<<c.ns, nt, 0, st>>>(a, MAX_SWEEPS, fail);
+        else jac_small_kernel<false><<<c.ns, nt, 0, st>>>(a, MAX_SWEEPS, fail);
+        count_launch();
+        int hfail = 0;
+        cudaError_t e = cudaMemcpyAsync(&hfail, fail, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("max_step: %s", cudaGetErrorString(e)); return done(CVXB_E_CUDA); }
+        if (hfail) { set_error("max_step: Jacobi eigensolver did not converge (non-finite input?)"); rc = 1; }
+        return done(rc);
+    }
+    {
+        const int gx = (int)std::min<size_t>(((size_t)c.maxs * c.maxs + 255) / 256, 1184);
+        jac_init_kernel<<<dim3(gx, c.ns), 256, 0, st>>>(a);
+        count_launch();
+    }
+    int flip = 0;
+    bool ok = false;
+    for (int sweep = 0; sweep <= MAX_SWEEPS; ++sweep) {
+        jac_off_kernel<<<c.ns, 256, 0, st>>>(a, flip);
+        count_launch();
+        cudaError_t e = cudaMemcpyAsync(hstats.data(), stats, hstats.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("max_step: %s", cudaGetErrorString(e)); return done(CVXB_E_CUDA); }
+        ok = true;
+        for (int k = 0; k < c.ns; ++k) {
+            if (c.s[k] && !jac_done(hstats[2 * k], hstats[2 * k + 1], prev[k], c.s[k])) ok = false;
+            prev[k] = hstats[2 * k];
+        }
+        if (ok || sweep == MAX_SWEEPS) break;
+        const dim3 blk(16, 16), grd((h + 15) / 16, (h + 15) / 16, c.ns);
+        for (int r = 0; r < a.N - 1; ++r) {
+            if (with_vectors) jac_round_kernel<true><<<grd, blk, 0, st>>>(a, r, flip);
+            else jac_round_kernel<false><<<grd, blk, 0, st>>>(a, r, flip);
+            count_launch();
+            flip ^= 1;
+        }
+    }
+    if (!ok) { set_error("max_step: Jacobi eigensolver did not converge (non-finite input?)"); return done(1); }
+    jac_sort_kernel<<<c.ns, 256, 0, st>>>(a, flip);
+    count_launch();
+    if (with_vectors) {
+        const int gx = (int)std::min<size_t>(((size_t)c.maxs * c.maxs + 255) / 256, 1184);
+        jac_vec_kernel<<<dim3(gx, c.ns), 256, 0, st>>>(a);
+        count_launch();
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("max_step: %s", cudaGetErrorString(e)); return done(CVXB_E_CUDA); }
+    return done(0);
+}
+
 int cvxb_max_step(double *x, const cvxb_dims *dims, double *sigma, double *result, int space) {
     if (!result) { set_error("max_step: result is NULL"); return CVXB_E_ARG; }
     cudaStream_t st; CVXB_TRY(vctx(&st));
     Lay L; CVXB_TRY(L.init(dims));
-    if (L.c.maxs > 0) {
-        (void)sigma;
-        set_error("max_step: 's' blocks need a symmetric eigensolver (reference dsyevr/dsyevd, "
-                  "misc_solvers.c:1132-1143): not built on the device yet");
-        return CVXB_E_UNSUP;
-    }
+    const int nlq = L.c.mnl + L.c.ml + L.c.sumq;
+    int sums = 0;
+    std::vector<int> sigoff(L.c.ns);
+    for (int k = 0; k < L.c.ns; ++k) { sigoff[k] = sums; sums += L.c.s[k]; }
     Buf xb;
     CVXB_TRY(xb.in(x, L.c.cdim, space, st));
-    double *d = nullptr;
+    double *d = nullptr, *dsig = nullptr;
+    int *dsigoff = nullptr;
+    auto done = [&](int r) { cudaFree(d); cudaFree(dsig); cudaFree(dsigoff); return r; };
     CVXB_CUDA(cudaMalloc(&d, sizeof(double)));
     max_step_kernel<<<1, 256, 0, st>>>(xb.dev, L.k, d);
     count_launch();
+    if (L.c.maxs > 0) {
+        // 's' blocks: lambda_min of each block (reference dsyevr_ range 'I' 1..1, or dsyevd_ 'V' when
+        // sigma is given: eigenvalues -> sigma, eigenvectors -> x; misc_solvers.c:1099-1150)
+        if (cudaMalloc(&dsig, (size_t)sums * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&dsigoff, (size_t)L.c.ns * sizeof(int)) != cudaSuccess ||
+            cudaMemcpyAsync(dsigoff, sigoff.data(), (size_t)L.c.ns * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("max_step: device allocation failed");
+            return done(CVXB_E_NOMEM);
+        }
+        int rc = sym_eig_blocks(L.c, xb.dev + nlq, dsig, dsigoff, sigma != nullptr, st);
+        if (rc) return done(rc);
+        max_step_s_kernel<<<1, 1, 0, st>>>(d, dsig, L.c.d_s, dsigoff, L.c.ns, nlq > 0);
+        count_launch();
+        if (sigma) {
+            if (cudaMemcpyAsync(sigma, dsig, (size_t)sums * sizeof(double),
+                                space == CVXB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+                set_error("max_step: copy of sigma failed");
+                return done(CVXB_E_CUDA);
+            }
+            int rc2 = xb.out(st);
+            if (rc2) return done(rc2);
+        }
+    }
     cudaError_t e = cudaMemcpyAsync(result, d, sizeof(double), cudaMemcpyDeviceToHost, st);
-    cudaStreamSynchronize(st);
-    cudaFree(d);
-    if (e != cudaSuccess) { set_error("max_step: %s", cudaGetErrorString(e)); return CVXB_E_CUDA; }
-    return 0;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("max_step: %s", cudaGetErrorString(e)); return done(CVXB_E_CUDA); }
+    return done(0);
 }
 
 }  // extern "C"

@@ -153,11 +153,17 @@ def sdot(x, y, dims, mnl=0):
 
 
 def max_step(x, dims, mnl=0, sigma=None):
-    """min {t | x + t*e >= 0}.  misc_solvers.c:1052-1153.  's' blocks (eigenvalues) are not built
-    on the device yet: NotImplementedError, use cvxopt.misc_solvers.max_step for those."""
+    """min {t | x + t*e >= 0}.  misc_solvers.c:1052-1153.  With `sigma` (a 'd' buffer of length
+    sum(dims['s'])) the eigenvalues of the 's' blocks are returned in sigma (ascending per block) and
+    their eigenvectors overwrite the 's' blocks of x, as the reference's dsyevd_ call does
+    (:1132-1136); eigenvector signs are the eigensolver's choice there and here."""
     lib = _lib.load()
     cd, keep, cdim, _ = make_dims(dims, mnl)
     xa = _vec(x, cdim, "x")
+    sp = None
+    if sigma is not None:
+        sa = _vec(sigma, sum(int(k) for k in dims["s"]), "sigma")
+        sp = sa.ctypes.data_as(_lib.c_double_p)
     out = C.c_double()
-    _lib.check(lib.cvxb_max_step(xa.ctypes.data, C.byref(cd), None, C.byref(out), _lib.HOST), "max_step")
+    _lib.check(lib.cvxb_max_step(xa.ctypes.data, C.byref(cd), sp, C.byref(out), _lib.HOST), "max_step")
     return out.value

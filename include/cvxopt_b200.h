@@ -30,7 +30,7 @@ extern "C" {
 #define CVXB_E_CUDA    (-2)   /* CUDA runtime error */
 #define CVXB_E_NOMEM   (-3)   /* allocation failure */
 #define CVXB_E_NOGPU   (-4)   /* no usable sm_100 device: the product path has NO CPU fallback */
-#define CVXB_E_UNSUP   (-5)   /* valid in the reference but not built yet (e.g. p > 0) */
+#define CVXB_E_UNSUP   (-5)   /* valid in the reference but not built on the device */
 
 /* memory space of the pointers handed to a call */
 #define CVXB_HOST   0
@@ -140,6 +140,9 @@ int cvxb_trisc(double *x, const cvxb_dims *dims, int space);                 /* 
 int cvxb_triusc(double *x, const cvxb_dims *dims, int space);                /* :940 */
 int cvxb_sdot(const double *x, const double *y, const cvxb_dims *dims, double *result,
               int space);                                                    /* :991 */
+/* sigma == NULL: x is read only.  sigma != NULL (sum of the 's' orders): the eigenvalues of every 's'
+ * block go to sigma (ascending) and its eigenvectors overwrite the block of x (:1132-1136).
+ * Returns 1 if the eigensolver does not converge (non-finite input). */
 int cvxb_max_step(double *x, const cvxb_dims *dims, double *sigma, double *result,
                   int space);                                                /* :1052 */
 

@@ -428,8 +428,9 @@ def sdot(x, y, dims, mnl=0):
     return a
 
 
-def max_step(x, dims, mnl=0):
-    """min {t | x + t e >= 0}, misc_solvers.c:1052-1153 (without the sigma output)."""
+def max_step(x, dims, mnl=0, sigma=None):
+    """min {t | x + t e >= 0}, misc_solvers.c:1052-1153.  With sigma: eigenvalues of the 's' blocks
+    -> sigma, eigenvectors -> the 's' blocks of x (dsyevd_ 'V', :1132-1136)."""
     ind = mnl + dims["l"]
     t = -np.finfo(np.float32).max
     if ind:
@@ -437,9 +438,16 @@ def max_step(x, dims, mnl=0):
     for mk in dims["q"]:
         t = max(t, float(np.linalg.norm(x[ind + 1:ind + mk]) - x[ind]))
         ind += mk
+    ind2 = 0
     for mk in dims["s"]:
         if mk:
-            w = np.linalg.eigvalsh(_symL(x[ind:ind + mk * mk], mk))
+            if sigma is None:
+                w = np.linalg.eigvalsh(_symL(x[ind:ind + mk * mk], mk))
+            else:
+                w, Q = np.linalg.eigh(_symL(x[ind:ind + mk * mk], mk))
+                sigma[ind2:ind2 + mk] = w
+                x[ind:ind + mk * mk] = Q.reshape(-1, order="F")
             t = max(t, -float(w[0]))
         ind += mk * mk
+        ind2 += mk
     return t if ind else 0.0

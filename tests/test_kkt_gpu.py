@@ -257,11 +257,66 @@ def test_misc_solvers_mirror_ipm_side(dims):
         f(x, dims); fo(xo, dims)
         assert np.array_equal(x, xo)
     x = rng.standard_normal(K)
-    if dims["s"]:
-        with pytest.raises(NotImplementedError):
-            ms.max_step(x, dims)
-    else:
-        assert abs(ms.max_step(x, dims) - ko.max_step(x, dims)) < 1e-13
+    assert abs(ms.max_step(x.copy(), dims) - ko.max_step(x.copy(), dims)) < 1e-12
+
+
+@pytest.mark.parametrize("dims", [{"l": 3, "q": [4], "s": [3, 8, 0, 1, 2]},      # one CTA per block (order <= 64)
+                                  {"l": 0, "q": [], "s": [64, 33]},
+                                  {"l": 2, "q": [], "s": [70, 5, 0, 1]},           # one launch per Jacobi round
+                                  {"l": 0, "q": [], "s": [129]}])
+def test_max_step_s_blocks_jacobi_eigensolver(dims):
+    """max_step on 's' blocks (misc_solvers.c:1099-1150): smallest eigenvalue without sigma (dsyevr_),
+    all eigenvalues + eigenvectors with sigma (dsyevd_ 'V').  Eigenvalues agree with LAPACK to
+    1e-12 * ||X||; the eigenvectors (unique only up to sign / rotation inside an eigenspace) are checked
+    through orthonormality and the reconstruction Q diag(sigma) Q' = X."""
+    from cvxopt_b200 import misc_solvers as ms
+    rng = np.random.Generator(np.random.PCG64(33))
+    K = cone_dim(dims)
+    x = rng.standard_normal(K)
+    x0 = x.copy()
+    t = ms.max_step(x, dims)
+    assert np.array_equal(x, x0)                      # without sigma x is not modified (:1139 copies)
+    assert abs(t - ko.max_step(x0.copy(), dims)) < 1e-12 * max(1.0, np.abs(x0).max() * max(dims["s"]))
+    ns = sum(dims["s"])
+    sig = np.full(ns, np.nan); sigo = np.zeros(ns)
+    xo = x0.copy()
+    t2 = ms.max_step(x, dims, sigma=sig)
+    to = ko.max_step(xo, dims, sigma=sigo)
+    assert abs(t2 - to) < 1e-12 * max(1.0, np.abs(x0).max() * max(dims["s"]))
+    nlq = dims["l"] + sum(dims["q"])
+    assert np.array_equal(x[:nlq], x0[:nlq])
+    off, o2 = nlq, 0
+    for mk in dims["s"]:
+        if mk:
+            X = x0[off:off + mk * mk].reshape(mk, mk, order="F")
+            X = np.tril(X) + np.tril(X, -1).T
+            scale_ = np.linalg.norm(X)
+            w = sig[o2:o2 + mk]
+            assert np.all(np.diff(w) >= 0)
+            assert np.abs(w - sigo[o2:o2 + mk]).max() < 1e-12 * scale_
+            Q = x[off:off + mk * mk].reshape(mk, mk, order="F")
+            assert np.abs(Q.T @ Q - np.eye(mk)).max() < 1e-12
+            assert np.abs(Q @ np.diag(w) @ Q.T - X).max() < 1e-12 * scale_
+        off += mk * mk; o2 += mk
+
+
+def test_max_step_s_blocks_special_matrices():
+    """already diagonal, zero, repeated eigenvalues, huge dynamic range, and a non-finite entry
+    (the Jacobi sweeps cannot converge: ArithmeticError, like a LAPACK info > 0)."""
+    from cvxopt_b200 import misc_solvers as ms
+    for X in (np.eye(6), np.zeros((4, 4)), np.diag([1.0, 1, 2, 2, 2]), np.ones((6, 6)),
+              np.diag([1e-200, 1.0, 1e200]), np.array([[1e300, 1e-300], [1e-300, -1e300]])):
+        mk = X.shape[0]
+        dims = {"l": 0, "q": [], "s": [mk]}
+        sig = np.zeros(mk)
+        x = X.reshape(-1, order="F").copy()
+        t = ms.max_step(x, dims, sigma=sig)
+        w = np.linalg.eigvalsh(X)
+        assert np.abs(sig - w).max() <= 1e-13 * max(np.abs(w).max(), 1e-300)
+        assert t == -sig[0]
+    bad = np.eye(5); bad[3, 1] = np.nan
+    with pytest.raises(ArithmeticError):
+        ms.max_step(bad.reshape(-1, order="F").copy(), {"l": 0, "q": [], "s": [5]})
 
 
 def test_no_cone_rows_and_handle_lifecycle():

@@ -176,6 +176,19 @@ def test_ipm_side_cone_algebra_matches_reference(ref, dims):
         X = x[k_off:k_off + k * k].reshape(k, k, order="F"); X[:] = (X + X.T) / 2
         x[k_off:k_off + k * k] = X.reshape(-1, order="F")
     np.testing.assert_allclose(ko.max_step(x.copy(), dims), misc.max_step(m(x), dims), rtol=1e-10, atol=1e-12)
+    ns = sum(dims["s"])
+    if ns:      # with sigma: eigenvalues in sigma, eigenvectors (up to sign) in the 's' blocks of x
+        from cvxopt import matrix
+        xo, sigo = x.copy(), np.zeros(ns)
+        xr, sigr = m(x), matrix(0.0, (ns, 1))
+        np.testing.assert_allclose(ko.max_step(xo, dims, sigma=sigo), misc.max_step(xr, dims, 0, sigr), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(sigo, np.array(sigr).ravel(), rtol=1e-10, atol=1e-11)
+        xr = np.array(xr).ravel()
+        off = dims["l"] + sum(dims["q"])
+        for k in dims["s"]:
+            Qo = xo[off:off + k * k].reshape(k, k, order="F"); Qr = xr[off:off + k * k].reshape(k, k, order="F")
+            np.testing.assert_allclose(np.abs(np.sum(Qo * Qr, axis=0)), np.ones(k), atol=1e-8)
+            off += k * k
     for fo, fr in ((ko.trisc, misc.trisc), (ko.triusc, misc.triusc)):
         x = rng.standard_normal(K); xr = m(x)
         fo(x, dims); fr(xr, dims)
