@@ -274,3 +274,29 @@ def kkt_chol(G, dims, A=None, mnl=0, H=None, device=0):
     so `factor(W)` / `factor(W, P)` do not re-upload n^2 doubles per iteration.
     """
     return KKTChol(G, dims, A, mnl, H, device)
+
+
+def kkt_chol2(G, dims, A=None, mnl=0, H=None, device=0):
+    """Drop-in for `misc.kkt_chol2(G, dims, A, mnl)` (reference misc.py:1352-1567), the drivers'
+    default for problems with only 'l' constraints (coneprog.py:458-462, 1805-1809).
+
+    S = H + GG' W^-1 W^-T GG = L L', K = A S^-1 A' = Lk Lk' (first-call fallback S += A'A when K
+    is singular, :1433-1447): exactly the elimination KKTChol runs, with diag(di) fused into the
+    SYRK operand load.  Same error as the reference for 'q'/'s' cones (:1384-1387)."""
+    if dims["q"] or dims["s"]:
+        raise ValueError("kktsolver option 'kkt_chol2' is implemented only for problems with no "
+                         "second-order or semidefinite cone constraints")
+    return KKTChol(G, dims, A, mnl, H, device)
+
+
+def kkt_ldl2(G, dims, A=None, mnl=0, H=None, device=0):
+    """Drop-in for `misc.kkt_ldl2(G, dims, A, mnl)` (reference misc.py:1128-1210): the 2x2 system
+
+        [ H + GG' W^-1 W^-T GG   A' ] [ux]   [bx + GG' W^-1 W^-T bz]
+        [ A                      0  ] [uy] = [by]
+
+    The reference factors it with sytrf (potrf when p = 0, :1172-1173).  The matrix is
+    quasi-definite, so its block L D L' with D = diag(I, -I) needs no pivoting:
+    L = [L11 0; A L11^-T  Lk] with S = L11 L11', A S^-1 A' = Lk Lk' -- which is the pair of
+    Cholesky factorizations KKTChol computes.  Same solution, all cones."""
+    return KKTChol(G, dims, A, mnl, H, device)

@@ -108,6 +108,38 @@ def test_equality_constraints(dims, n, p, with_H):
     fac.close()
 
 
+@pytest.mark.parametrize("name,dims,p", [("kkt_chol2", {"l": 90, "q": [], "s": []}, 0),
+                                         ("kkt_chol2", {"l": 90, "q": [], "s": []}, 11),
+                                         ("kkt_ldl2", {"l": 30, "q": [8, 5], "s": [6]}, 0),
+                                         ("kkt_ldl2", {"l": 30, "q": [8, 5], "s": [6]}, 9)])
+def test_chol2_and_ldl2_factory_names(name, dims, p):
+    """cvxopt_b200.kkt_chol2 / kkt_ldl2 (misc.py:1352 / :1128): same call protocol, same solution as the
+    oracle (pinned to the reference's kkt_chol2 / kkt_ldl2 by tests/test_oracle_vs_reference.py)."""
+    import cvxopt_b200
+    n = 45
+    rng = np.random.Generator(np.random.PCG64(5))
+    K = cone_dim(dims)
+    G = np.asfortranarray(rng.standard_normal((K, n)))
+    A = np.asfortranarray(rng.standard_normal((p, n))) if p else None
+    B = rng.standard_normal((n, n))
+    H = np.asfortranarray(B @ B.T / n + np.eye(n))
+    W, _ = random_scaling(dims, seed=6)
+    fac = getattr(cvxopt_b200, name)(G, dims, A)
+    solve = fac(W, H)
+    f_or = ko.KktChol(G, dims, A).factor(W, H)
+    x, y, z = rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(K)
+    xo, yo, zo = x.copy(), y.copy(), z.copy()
+    solve(x, y if p else None, z)
+    f_or(xo, yo if p else None, zo)
+    assert relerr(x, xo) < 1e-9
+    if p:
+        assert relerr(y, yo) < 1e-9
+    assert relerr(packed(z, dims), packed(zo, dims)) < 1e-9
+    fac.close()
+    with pytest.raises(ValueError):
+        cvxopt_b200.kkt_chol2(G, {"l": 0, "q": [4], "s": []}, None)
+
+
 def test_indefinite_raises_arithmetic_error():
     import cvxopt_b200
     n = 40

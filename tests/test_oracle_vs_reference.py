@@ -136,6 +136,42 @@ def test_kkt_chol_with_equalities_matches_reference(ref, dims, with_H):
     np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-11)
 
 
+@pytest.mark.parametrize("solver", ["kkt_ldl2", "kkt_chol2"])
+@pytest.mark.parametrize("p", [0, 3])
+@pytest.mark.parametrize("dims", DIMS)
+def test_same_system_as_reference_ldl2_and_chol2(ref, dims, p, solver):
+    """kkt_ldl2 (misc.py:1128) and kkt_chol2 (misc.py:1352) solve the system kkt_chol solves: the oracle's
+    elimination agrees with both, which is what lets cvxopt_b200.kkt_ldl2 / kkt_chol2 share the device path."""
+    from cvxopt import misc
+    if solver == "kkt_chol2" and (dims["q"] or dims["s"]):
+        with pytest.raises(ValueError):
+            misc.kkt_chol2(ref.matrix(0.0, (cone_dim(dims), 4)), dims, ref.matrix(0.0, (0, 4)))
+        return
+    n = 8
+    rng = np.random.Generator(np.random.PCG64(41))
+    K = cone_dim(dims)
+    G = np.asfortranarray(rng.standard_normal((K, n)))
+    A = np.asfortranarray(rng.standard_normal((p, n)))
+    B = rng.standard_normal((n, n))
+    H = np.asfortranarray(B @ B.T + np.eye(n))
+    W, _ = random_scaling(dims, seed=5)
+    f_or = ko.KktChol(G, dims, A if p else None).factor(W, H)
+    f_ref = getattr(misc, solver)(ref.matrix(G), dims, ref.matrix(A) if p else ref.matrix(0.0, (0, n)))(
+        to_ref_W(ref, W), ref.matrix(H))
+    x, y, z = rng.standard_normal(n), rng.standard_normal(p), rng.standard_normal(K)
+    xr, yr, zr = ref.matrix(x), ref.matrix(y, (p, 1)), ref.matrix(z)
+    f_or(x, y if p else None, z)
+    f_ref(xr, yr, zr)
+    np.testing.assert_allclose(x, np.array(xr).ravel(), rtol=1e-9, atol=1e-11)
+    if p:
+        np.testing.assert_allclose(y, np.array(yr).ravel(), rtol=1e-9, atol=1e-11)
+    _, _, _, _, cp = ko.cone_sizes(dims)
+    a, b = np.zeros(cp), np.zeros(cp)
+    ko.pack(z, a, dims)
+    ko.pack(np.array(zr).ravel(), b, dims)
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-11)
+
+
 @pytest.mark.parametrize("dims", DIMS)
 def test_ipm_side_cone_algebra_matches_reference(ref, dims):
     """scale2 / sprod / sinv / sdot / max_step / trisc / triusc restatements vs misc_solvers."""
