@@ -70,6 +70,8 @@ _SIGS = {
     "cvxb_max_step": (C.c_int, [C.c_void_p, C.POINTER(Dims), c_double_p, c_double_p, C.c_int]),
     "cvxb_syrk_scaled": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "cvxb_syrk_scaled_i8": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "cvxb_potrf": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "cvxb_potrs": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "cvxb_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,

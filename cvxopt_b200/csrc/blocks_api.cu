@@ -83,6 +83,24 @@ int cvxb_syrk_scaled(int n, int k, const double *A, int lda, const double *rowsc
     return 0;
 }
 
+int cvxb_syrk_scaled_i8(int n, int k, const double *A, int lda, const double *d, const double *H, int ldh,
+                        double *C, int ldc, int slices, int device) {
+    DevCtx *ctx; CVXB_TRY(get_ctx(device, &ctx));
+    void *work = nullptr;
+    if (slices < 1 || slices > 9) { set_error("syrk_scaled_i8: slices must be 1..9"); return CVXB_E_ARG; }
+    if (cudaMalloc(&work, ozaki_workspace_bytes(n, k, slices)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("syrk_scaled_i8: out of device memory for the slice workspace");
+        return CVXB_E_NOMEM;
+    }
+    int rc = ozaki_syrk(n, k, A, lda, d, H, ldh, 1.0, C, ldc, slices, 0, work, nullptr, ctx->st);
+    cudaError_t e = cudaStreamSynchronize(ctx->st);
+    cudaFree(work);
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_error("syrk_scaled_i8: %s", cudaGetErrorString(e)); return CVXB_E_CUDA; }
+    return 0;
+}
+
 int cvxb_potrf(int n, double *A, int lda, double *work_inv, int device) {
     DevCtx *ctx; CVXB_TRY(get_ctx(device, &ctx));
     CVXB_TRY(potrf_lower(n, A, lda, work_inv, ctx->cw, ctx->st));

@@ -113,6 +113,12 @@ int dmma_gemm(const GemmDesc &g, cudaStream_t st);
 size_t dmma_gemm_splitk_ws_doubles();   // workspace size for GemmDesc::splitk_ws
 int dmma_gemm_tile_cols();              // width of a c tile (units of ct_begin / ct_end)
 
+// ozaki_syrk.cu (experimental): C(lower) = A' diag(d)^2 A + beta*D through int8 slices on tcgen05
+size_t ozaki_workspace_bytes(int n, int m, int S);
+int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, const double *D,
+               long long ldd, double beta, double *C, long long ldc, int S, int layout, void *work,
+               unsigned int *dbg, cudaStream_t st);
+
 // Cholesky (lower) of the n x n matrix A in place; inv receives the inverses of the
 // NB x NB diagonal blocks of L (block j at inv + j*NB*NB, leading dimension NB).
 // info (device int) = first non-positive pivot (1-based) or 0.
