@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "kkt_factor_solve_gflops_fp64"
+INT8_TENSOR_PEAK_TOPS = 4500.0      # nominal dense int8 (B200); no measured entry yet
 FP64_DMMA_PEAK_TFLOPS = 37.2   # tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peaks.md)
 
 
@@ -258,6 +259,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ipm", action="store_true", help="skip the full-IPM and batch extras")
     ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--no-i8", action="store_true", help="skip the extra leg on the experimental int8-slice SYRK")
     args = ap.parse_args()
     if args.m <= 0:
         args.m = 2 * args.n
@@ -280,6 +282,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, m = args.n, args.m
+    # csrc/kkt_api.cu: the 'l'-row SYRK of large problems runs on the int8 tensor path unless CVXB_OZAKI=0
+    oz_env = os.environ.get("CVXB_OZAKI", "1")[:1]
+    i8_default = (oz_env == "2") or (oz_env == "1" and n >= 4096 and m >= 8192)
     f_fac, f_sol, f_it = flops(n, m)
     P, G, d, rng = make_problem(n, m, args.seed + rank)
     dims = {"l": m, "q": [], "s": []}
@@ -364,6 +369,33 @@ def main():
         syrk = float(np.mean(syrk_ms))
         f_syrk = float(n) * n * m
         achieved = f_syrk / (syrk * 1e-3) * 1e-12
+        if i8_default:
+            # the 'l'-row SYRK ran as 45 exact int8 products (nine radix-2^7 slices per entry) on
+            # tcgen05.mma kind::i8: the bounding pipe is the int8 tensor pipe.  syrk_ms covers the slicing
+            # kernels (~1 ms) as well as oz_mma_kernel, so `achieved` is a lower bound for the kernel alone.
+            tiles = ((n + 127) // 128) * ((n + 127) // 128 + 1) // 2
+            i8_ops = 45.0 * 2.0 * tiles * 128.0 * 128.0 * m
+            a8 = i8_ops / (syrk * 1e-3) * 1e-12
+            roofline = {"kernel": "oz_mma_kernel (int8-slice SYRK: tcgen05.mma.kind::i8, int32 accumulators in TMEM)",
+                        "bound": "tensor", "achieved": a8, "peak": INT8_TENSOR_PEAK_TOPS, "unit": "TFLOP/s",
+                        "frac": a8 / INT8_TENSOR_PEAK_TOPS,
+                        "peak_source": "nominal dense int8 rate of B200 (4.5 POP/s; MEASURED_PEAKS.json has no int8 entry); "
+                                       "`achieved` counts int8 multiply-add ops of the 45 slice products",
+                        "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+                        # dram read + write of one launch from the ncu capture of the first version of the
+                        # kernel (same operand streams; profiles/r01k_ozaki_syrk_ncu_summary.md), n=8192 only
+                        "traffic": (14.40e9 + 0.80e9) if (n == 8192 and m == 16384) else None,
+                        "algorithmic_bytes": 8.0 * m * n + 9.0 * m * n * 2 + 8.0 * n * n}
+        else:
+            roofline = {"kernel": "dmma_gemm_kernel<XK,YK,VEC> (fused NT-scaled SYRK)", "bound": "tensor",
+                        "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                        "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
+                        "peak_source": "measured DMMA.8x8x4 pipe rate on this pool (tools/fp64_peak.cu; "
+                                       "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 = 35.4)",
+                        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
+                        # committed capture profiles/r01j_syrk_band_order_dram.md (n=8192 only)
+                        "traffic": (7.30e9 + 0.275e9) if (n == 8192 and m == 16384) else None,
+                        "algorithmic_bytes": 8.0 * m * n + 8.0 * n * n}
         out = {
             "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -371,7 +403,9 @@ def main():
             "config": {"workload": "dense QP KKT step n=%d m=%d ('l' cone): 1 factor + 2 solves" % (n, m),
                        "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (G = %.2f GB, K = %.2f GB)" % (8.0 * n * m / 1e9, 8.0 * n * n / 1e9),
-                       "flops_per_step": f_it},
+                       "flops_per_step": f_it,
+                       "syrk_path": ("9 int8 slices per entry on tcgen05.mma kind::i8 (exact int32 products, fp64 recombination)"
+                                     if i8_default else "fp64 DMMA")},
             "e2e": {"value": e2e_val, "unit": "GF/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
@@ -379,23 +413,53 @@ def main():
             "breakdown_ms": {"factor": float(np.mean(fac_ms)), "syrk": syrk, "potrf": float(np.mean(potrf_ms)),
                              "solve_each": float(np.mean(sol_ms))},
             "ipm_iters_per_s_kkt_bound": 1e3 / ms_step,
-            "roofline": {"kernel": "dmma_gemm_kernel<XK,YK,VEC> (fused NT-scaled SYRK)", "bound": "tensor",
-                         "achieved": achieved, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
-                         "peak_source": "measured DMMA.8x8x4 pipe rate on this pool (tools/fp64_peak.cu; "
-                                        "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 = 35.4)",
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
-                         # committed capture profiles/r01j_syrk_band_order_dram.md (n=8192 only; 11.3 GB
-                         # before the band-major tile order, profiles/r01d_syrk_n8192_ncu_summary.md)
-                         "traffic": (7.30e9 + 0.275e9) if (n == 8192 and m == 16384) else None,
-                         "algorithmic_bytes": 8.0 * m * n + 8.0 * n * n},
+            "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(args, P, G, d)
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_i8:
+        # extra leg (not the headline): the same KKT step with the 'l'-row SYRK on the other tensor path
+        # (fp64 DMMA kernel when the int8-slice kernel is the default, and vice versa), timed the same way,
+        # and its direction against the default path's
+        saved = os.environ.get("CVXB_OZAKI")
+        os.environ["CVXB_OZAKI"] = "0" if i8_default else "2"
+        kkt8 = cvxopt_b200.kkt_chol(G, dims, None, H=P, device=local_rank)
+        if saved is None:
+            os.environ.pop("CVXB_OZAKI")
+        else:
+            os.environ["CVXB_OZAKI"] = saved
+
+        def step8():
+            kkt8.factor_ptr(d=d_d.data_ptr(), di=d_di.data_ptr(), space=_lib.DEVICE)
+            for i in range(2):
+                xw.copy_(xs[i]); zw.copy_(zs[i])
+                torch.cuda.current_stream().synchronize()
+                kkt8.solve_ptr(xw.data_ptr(), zw.data_ptr(), space=_lib.DEVICE)
+        for _ in range(3):
+            step8()
+        x8 = xw.clone()
+        step_dev()
+        xdiff = float((torch.linalg.vector_norm(x8 - xw) / torch.linalg.vector_norm(xw)).item())
+        torch.cuda.synchronize()
+        k8 = max(3, min(args.steps, 10))
+        s8 = []
+        kkt8.timer_start()
+        for _ in range(k8):
+            step8()
+            s8.append(kkt8.last_breakdown()["syrk_ms"])
+        ms8 = kkt8.timer_stop() / k8
+        extras["other_syrk_path"] = {
+            "what": ("fp64 DMMA SYRK (CVXB_OZAKI=0)" if i8_default else "int8-slice SYRK on tcgen05.mma kind::i8 (CVXB_OZAKI=2)")
+                    + ": same step, same inputs",
+            "ms_per_step": ms8, "value": f_it / (ms8 * 1e-3) * 1e-9, "syrk_ms": float(np.mean(s8)),
+            "syrk_fp64_equiv_tflops": float(n) * n * m / (float(np.mean(s8)) * 1e-3) * 1e-12,
+            "direction_rel_diff_vs_default": xdiff}
+        kkt8.close()
+        del kkt8
     kkt.close()
     del kkt, d_d, d_di, xs, zs
     torch.cuda.empty_cache()
-    extras = {}
     if not args.no_ipm:
         # (ii) IPM iterations/s: a whole solve of the same-size QP, device resident
         if rank == 0:

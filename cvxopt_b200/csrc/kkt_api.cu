@@ -6,6 +6,7 @@
 // uploaded once and stay resident in HBM; per factor only the O(cdim) scaling
 // parameters cross PCIe, per solve only the right-hand side / solution.
 #include "cone.cuh"
+#include <cstdlib>
 #include <cstdarg>
 #include <mutex>
 
@@ -88,6 +89,11 @@ struct cvxb_kkt {
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, t0 = nullptr, t1 = nullptr;
     double factor_ms = 0, solve_ms = 0, br[3] = {0, 0, 0};
     bool factored = false;
+    // SYRK of the 'l' rows on the int8 tensor path (ozaki_syrk.cu): 0 off (DMMA kernel), 1 for large
+    // problems (where it measured faster), 2 always.  CVXB_OZAKI=0/1/2 read at create; unset = 1.
+    int i8_mode = 1;
+    void *oz_work = nullptr;
+    size_t oz_bytes = 0;
 };
 
 namespace {
@@ -154,6 +160,7 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     CVXB_TRY(check_device(device));
     cvxb_kkt *k = new cvxb_kkt();
     k->device = device; k->n = n; k->p = p;
+    if (const char *e = getenv("CVXB_OZAKI")) k->i8_mode = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
     int rc = k->cone.init(dims);
     if (rc) { delete k; return rc; }
     const ConeLayout &c = k->cone;
@@ -241,6 +248,7 @@ void cvxb_kkt_destroy(cvxb_kkt *k) {
     double *bufs[] = {k->Aeq, k->Asct, k->Kp, k->invp, k->yd, k->Hres, k->Hbuf, k->Kmat, k->inv, k->Gs, k->Gunp, k->Dfbuf, k->bzp,
                       k->zin, k->zt, k->xv, k->yv, k->gemv_ws, k->swork};
     for (double *b : bufs) if (b) cudaFree(b);
+    if (k->oz_work) cudaFree(k->oz_work);
     k->W.destroy();
     k->cone.destroy();
     chol_work_destroy(k->cw);
@@ -319,7 +327,24 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
     int info = 0;
     auto assemble_and_factor = [&](bool add_ata) -> int {
         bool have = false;
-        if (c.ml > 0 && n > 0) {
+        const bool i8 = k->i8_mode == 2 || (k->i8_mode == 1 && n >= 4096 && c.ml >= 8192);
+        if (c.ml > 0 && n > 0 && i8) {
+            // G_l' diag(di)^2 G_l + H from nine int8 slices per entry (exact products, fp64-level result)
+            const size_t need = ozaki_workspace_bytes(n, c.ml, 9);
+            if (need > k->oz_bytes) {
+                if (k->oz_work) cudaFree(k->oz_work);
+                k->oz_work = nullptr; k->oz_bytes = 0;
+                if (cudaMalloc(&k->oz_work, need) != cudaSuccess) {
+                    cudaGetLastError();
+                    set_error("factor: out of device memory for the int8 slice workspace (%zu bytes)", need);
+                    return CVXB_E_NOMEM;
+                }
+                k->oz_bytes = need;
+            }
+            CVXB_TRY(ozaki_syrk(n, c.ml, k->G + c.mnl, k->ldg, k->W.di, Hptr, ldH, 1.0, k->Kmat, ldk, 9, 0,
+                                k->oz_work, nullptr, st));
+            have = true;
+        } else if (c.ml > 0 && n > 0) {
             GemmDesc g;
             g.M = n; g.N = n; g.K = c.ml;
             g.X = k->G + c.mnl; g.ldx = (int)k->ldg; g.x_kmajor = true;

@@ -1,7 +1,9 @@
 // fp64 SYRK  C = A' diag(d)^2 A (+ H)  on the int8 tensor path (tcgen05.mma kind::i8, int32
-// accumulators in TMEM) by error-free slicing (Ozaki scheme).  EXPERIMENTAL, opt-in: the product
-// path (kkt_api.cu) stays on the DMMA kernel unless CVXB_OZAKI=1.  Replaces the same reference call
-// as the DMMA SYRK: blas.syrk(Gs, K, trans='T') in misc.kkt_chol.factor (misc.py:1275, blas.c:3039).
+// accumulators in TMEM) by error-free slicing (Ozaki scheme).  kkt_api.cu uses it for the 'l'-row SYRK
+// of large problems (n >= 4096, ml >= 8192; CVXB_OZAKI=0 keeps the DMMA kernel, =2 forces it at any
+// size).  Replaces the same reference call as the DMMA SYRK: blas.syrk(Gs, K, trans='T') in
+// misc.kkt_chol.factor (misc.py:1275, blas.c:3039).  Measured: 18.5 ms at n=8192, m=16384 against
+// 33.7 ms on the fp64 DMMA pipe, result within 4e-16 * sum|terms| of an 80-bit evaluation.
 //
 // Arithmetic.  Column j of Gs = diag(d) A is written  Gs[k,j] = 2^e_j * sum_s q_s[k,j] 2^-(6+7s),
 // q_s integers in [-64, 64] (round-to-nearest digits, radix 2^7, e_j from the column maximum), so
@@ -21,6 +23,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cmath>
+#include <vector>
+#include <algorithm>
 
 namespace cvxb {
 
@@ -30,9 +34,10 @@ constexpr int OZ_SMAX = 9;
 constexpr int OZ_T = 128;                 // tile edge (rows and columns of C)
 constexpr int OZ_KS = 32;                 // K rows per MMA (32 bytes of int8)
 constexpr int OZ_UNIT = OZ_T * OZ_KS;     // 4096 B
-constexpr int OZ_STAGES = 3;
-constexpr int OZ_STAGE_BYTES = 2 * OZ_SMAX * OZ_UNIT;          // A slices | B slices
-constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + 1024 + 256;
+constexpr int OZ_RING = 54;                // 4 KB units in the shared-memory ring (216 KB)
+constexpr int OZ_MAXST = 8;                // most stages a pass may split the ring into
+constexpr int OZ_MAXPASS = 5;
+constexpr int OZ_SMEM = OZ_RING * OZ_UNIT + 1024 + 256;
 constexpr int OZ_THREADS = 192;
 constexpr int OZ_KRANGE = 32768 / OZ_KS;  // k steps per drain (int32 overflow bound)
 
@@ -52,6 +57,9 @@ struct OzParams {
     double beta;
     int n, nblk, nk, S;
     int layout;                // 0: SW32; 1: none (SBO 256, LBO 128); 2: none (SBO 128, LBO 256)
+    int npass;                 // level groups: pass ps accumulates levels pd0[ps] .. pd1[ps] (<= 4 of them)
+    int pd0[OZ_MAXPASS], pd1[OZ_MAXPASS];
+    const unsigned int *tiles; // (I << 16) | J per CTA, in launch order
     unsigned int *dbg;         // optional progress words (mapped host memory) or nullptr
 };
 
@@ -104,6 +112,16 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// one lane of a converged warp (the pattern the compiler recognises for single-thread tcgen05 issue)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void dbg_put(const OzParams &p, int slot, unsigned int v) {
@@ -117,24 +135,40 @@ __device__ __forceinline__ void dbg_put(const OzParams &p, int slot, unsigned in
 // D = s32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N/8 << 17, M/16 << 24
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((OZ_T / 8) << 17) | ((OZ_T / 16) << 24);
 
+// One k step of a pass whose level range is known at compile time: a straight-line MMA sequence
+// (the tensor pipe retires a 128x128x32 int8 MMA every 64 cycles; a runtime pair loop issues too slowly).
+// The first k step of a pass overwrites each accumulator with its first product (s == 0), later ones add.
+template <int D0, int D1, bool FIRST>
+__device__ __forceinline__ void oz_issue_step(uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t tmem_base) {
+    constexpr int NS = D1 + 1;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s * (OZ_UNIT >> 4));
+#pragma unroll
+        for (int tt = 0; tt < NS; ++tt) {
+            if (s + tt >= D0 && s + tt <= D1) {
+                const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(b_lo + tt * (OZ_UNIT >> 4));
+                tc_mma_i8(tmem_base + (s + tt - D0) * OZ_T, da, db, OZ_IDESC, (FIRST && s == 0) ? 0u : 1u);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
     __shared__ uint32_t tmem_base_sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OZ_STAGES * OZ_STAGE_BYTES);
-    uint64_t *full = bars, *empty = bars + OZ_STAGES, *acc_full = bars + 2 * OZ_STAGES,
-             *acc_empty = bars + 2 * OZ_STAGES + 1;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OZ_RING * OZ_UNIT);
+    uint64_t *full = bars, *empty = bars + OZ_MAXST, *acc_full = bars + 2 * OZ_MAXST,
+             *acc_empty = bars + 2 * OZ_MAXST + 1;
 
     // lower-triangular tile (I >= J) of this CTA
-    const int t = blockIdx.x;
-    int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((long long)I * (I + 1) / 2 > t) --I;
-    while ((long long)(I + 1) * (I + 2) / 2 <= t) ++I;
-    const int J = t - (int)((long long)I * (I + 1) / 2);
+    const unsigned int tl = p.tiles[blockIdx.x];
+    const int I = (int)(tl >> 16), J = (int)(tl & 0xFFFFu);
 
     if (tid == 0) {
-        for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < OZ_MAXST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,66 +185,97 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
     dbg_put(p, 0, 0x100u + (tid == 0));
 
     const int S = p.S;
-    const int npass = (S + 3) / 4;
+    const int npass = p.npass;
     const int nrange = (p.nk + OZ_KRANGE - 1) / OZ_KRANGE;
+    // Stage geometry of a pass: nS slices of A then nS slices of B per k step; the ring is cut into
+    // as many such stages as fit (deeper prefetch for the passes that need few slices).
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== producer: one bulk copy per operand per k step =====
-            int st = 0; uint32_t ph = 0;
+            uint32_t filled = 0, epar = 0;               // per stage: ever filled / parity of its last release
             for (int rg = 0; rg < nrange; ++rg) {
                 const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
                 for (int ps = 0; ps < npass; ++ps) {
-                    const int nS = min(S, 4 * ps + 4);
+                    const int nS = min(S, p.pd1[ps] + 1);
+                    const int nst = min(OZ_MAXST, OZ_RING / (2 * nS));
                     const uint32_t bytes = (uint32_t)nS * OZ_UNIT;
+                    // the new geometry overlaps the old stages: wait until every one of them is released
+                    for (int s2 = 0; s2 < OZ_MAXST; ++s2)
+                        if ((filled >> s2) & 1u) mbar_wait(empty + s2, (epar >> s2) & 1u);
+                    int st = 0;
                     for (int kc = k0; kc < k1; ++kc) {
-                        mbar_wait(empty + st, ph ^ 1);
+                        if ((filled >> st) & 1u) { mbar_wait(empty + st, (epar >> st) & 1u); epar ^= 1u << st; }
+                        else filled |= 1u << st;
                         mbar_expect_tx(full + st, 2 * bytes);
-                        uint8_t *sa = smem + st * OZ_STAGE_BYTES;
+                        uint8_t *sa = smem + (size_t)st * 2 * bytes;
                         bulk_g2s(sa, p.Q + ((size_t)I * p.nk + kc) * (size_t)S * OZ_UNIT, bytes, full + st);
-                        bulk_g2s(sa + OZ_SMAX * OZ_UNIT, p.Q + ((size_t)J * p.nk + kc) * (size_t)S * OZ_UNIT, bytes, full + st);
-                        if (++st == OZ_STAGES) { st = 0; ph ^= 1; }
+                        bulk_g2s(sa + bytes, p.Q + ((size_t)J * p.nk + kc) * (size_t)S * OZ_UNIT, bytes, full + st);
+                        if (++st == nst) st = 0;
                     }
                 }
             }
             dbg_put(p, 1, 0x200u);
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            uint32_t hi, lbo16;
-            if (p.layout == 0) { hi = (256u >> 4) | (1u << 14) | (6u << 29); lbo16 = 0; }
-            else if (p.layout == 1) { hi = (256u >> 4) | (1u << 14); lbo16 = 128u >> 4; }
-            else { hi = (128u >> 4) | (1u << 14); lbo16 = 256u >> 4; }
-            int st = 0; uint32_t ph = 0;
-            int g = 0;                                   // global pass counter (for the accumulator barriers)
-            for (int rg = 0; rg < nrange; ++rg) {
-                const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
-                for (int ps = 0; ps < npass; ++ps, ++g) {
-                    const int nS = min(S, 4 * ps + 4), d0 = 4 * ps, d1 = min(S - 1, d0 + 3);
-                    if (g > 0) { mbar_wait(acc_empty, (uint32_t)(g - 1) & 1); tc_fence_after(); }
-                    uint32_t touched = 0;
-                    for (int kc = k0; kc < k1; ++kc) {
-                        mbar_wait(full + st, ph);
-                        tc_fence_after();
-                        const uint32_t a0 = smem_u32(smem + st * OZ_STAGE_BYTES);
-                        const uint32_t b0 = a0 + OZ_SMAX * OZ_UNIT;
-                        for (int s = 0; s < nS; ++s) {
-                            const int tlo = max(0, d0 - s), thi = min(nS - 1, d1 - s);
-                            const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
-                            for (int tt = tlo; tt <= thi; ++tt) {
-                                const int lev = s + tt - d0;
-                                const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)((((b0 + tt * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
-                                tc_mma_i8(tmem_base + lev * OZ_T, da, db, OZ_IDESC, (touched >> lev) & 1u);
-                                touched |= 1u << lev;
+        // ===== MMA issuer: the whole warp runs the loop (uniform control flow and addresses),
+        // lane 0 issues the tcgen05 instructions =====
+        uint32_t hi, lbo16;
+        if (p.layout == 0) { hi = (256u >> 4) | (1u << 14) | (6u << 29); lbo16 = 0; }
+        else if (p.layout == 1) { hi = (256u >> 4) | (1u << 14); lbo16 = 128u >> 4; }
+        else { hi = (128u >> 4) | (1u << 14); lbo16 = 256u >> 4; }
+        uint32_t cpar = 0;                           // per stage: parity of its next fill
+        int g = 0;                                   // global pass counter (for the accumulator barriers)
+        const uint32_t sbase = smem_u32(smem);
+        for (int rg = 0; rg < nrange; ++rg) {
+            const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
+            for (int ps = 0; ps < npass; ++ps, ++g) {
+                const int d0 = p.pd0[ps], d1 = p.pd1[ps];
+                const int nS = min(S, d1 + 1);
+                const int nst = min(OZ_MAXST, OZ_RING / (2 * nS));
+                const uint32_t bytes = (uint32_t)nS * OZ_UNIT;
+                const int code = (p.layout == 0 && nS == d1 + 1) ? d0 * 16 + d1 : -1;
+                if (g > 0) { mbar_wait(acc_empty, (uint32_t)(g - 1) & 1); tc_fence_after(); }
+                uint32_t touched = 0;
+                int st = 0;
+                for (int kc = k0; kc < k1; ++kc) {
+                    mbar_wait(full + st, (cpar >> st) & 1u);
+                    cpar ^= 1u << st;
+                    tc_fence_after();
+                    const uint32_t a0 = sbase + (uint32_t)st * 2u * bytes;
+                    const uint32_t b0 = a0 + bytes;
+                    const bool firstk = (kc == k0);
+                    if (elect_one()) {
+#define OZ_CASE(D0, D1)                                                                              \
+    case (D0) * 16 + (D1):                                                                           \
+        if (firstk) oz_issue_step<D0, D1, true>(a0 >> 4, b0 >> 4, hi, tmem_base);                    \
+        else oz_issue_step<D0, D1, false>(a0 >> 4, b0 >> 4, hi, tmem_base);                          \
+        break;
+                        switch (code) {
+                            OZ_CASE(0, 0) OZ_CASE(1, 4) OZ_CASE(5, 8)          // S = 9: {0} {1..4} {5..8}
+                            OZ_CASE(0, 1) OZ_CASE(2, 4)                         // S = 9: {0,1} {2..4} {5..8}
+                            OZ_CASE(0, 3) OZ_CASE(4, 7)                         // S = 8: {0..3} {4..7}
+                            OZ_CASE(2, 5) OZ_CASE(6, 8) OZ_CASE(8, 8)
+                        default:
+                            for (int s = 0; s < nS; ++s) {
+                                const int tlo = max(0, d0 - s), thi = min(nS - 1, d1 - s);
+                                const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
+                                for (int tt = tlo; tt <= thi; ++tt) {
+                                    const int lev = s + tt - d0;
+                                    const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)((((b0 + tt * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
+                                    tc_mma_i8(tmem_base + lev * OZ_T, da, db, OZ_IDESC, (touched >> lev) & 1u);
+                                    touched |= 1u << lev;
+                                }
                             }
                         }
+#undef OZ_CASE
                         tc_commit(empty + st);           // frees the stage when these MMAs have read it
-                        if (++st == OZ_STAGES) { st = 0; ph ^= 1; }
                     }
-                    tc_commit(acc_full);
-                    dbg_put(p, 2, 0x300u + g);
+                    __syncwarp();
+                    if (++st == nst) st = 0;
                 }
+                if (elect_one()) { tc_commit(acc_full); dbg_put(p, 2, 0x300u + g); }
+                __syncwarp();
             }
         }
     } else {
@@ -222,7 +287,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
         int g = 0;
         for (int rg = 0; rg < nrange; ++rg) {
             for (int ps = 0; ps < npass; ++ps, ++g) {
-                const int d0 = 4 * ps, nlev = min(4, S - d0);
+                const int d0 = p.pd0[ps], nlev = p.pd1[ps] - d0 + 1;
                 mbar_wait(acc_full, (uint32_t)g & 1);
                 tc_fence_after();
                 // 2^(-12 - 7*(d0 + nlev - 1)): scale of the last level of the pass
@@ -324,9 +389,56 @@ __global__ void __launch_bounds__(OZ_T) oz_slice_kernel(int m, int n, const doub
 
 }  // namespace
 
+// level groups of <= 4 (TMEM holds four 128-column accumulators) minimising the modelled time
+// sum_p max(operand bytes / L2 rate, MMA cycles); CVXB_OZ_GROUPS="2,4,3" overrides
+static void oz_choose_groups(int S, int *npass, int *pd0, int *pd1) {
+    if (const char *e = getenv("CVXB_OZ_GROUPS")) {
+        int d = 0, np = 0;
+        const char *q = e;
+        while (*q && np < OZ_MAXPASS) {
+            const int len = atoi(q);
+            if (len < 1 || len > 4 || d + len > S) break;
+            pd0[np] = d; pd1[np] = d + len - 1; d += len; ++np;
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (d == S) { *npass = np; return; }
+    }
+    if (S == 9) {        // measured on B200 (n=8192, m=16384): {0,1} {2..4} {5..8} 18.5 ms, {0} {1..4} {5..8} 18.9, {0..3} {4..7} {8} 18.9
+        *npass = 3; pd0[0] = 0; pd1[0] = 1; pd0[1] = 2; pd1[1] = 4; pd0[2] = 5; pd1[2] = 8;
+        return;
+    }
+    double best = 1e300;
+    int bestcode = 0, bestn = 0;
+    // compositions of S into parts 1..4, at most OZ_MAXPASS parts: code = base-5 digits
+    for (int np = 1; np <= OZ_MAXPASS; ++np) {
+        int lim = 1;
+        for (int i = 0; i < np; ++i) lim *= 4;
+        for (int code = 0; code < lim; ++code) {
+            int c = code, d = 0;
+            double cost = 0;
+            for (int i = 0; i < np; ++i) {
+                const int len = 1 + c % 4; c /= 4;
+                const int d0 = d, d1 = d + len - 1;
+                d += len;
+                if (d > S) { cost = 1e300; break; }
+                const int nS = d1 + 1;
+                double mm = 0;
+                for (int l = d0; l <= d1; ++l) mm += l + 1;
+                cost += std::max(2.0 * nS * OZ_UNIT / 42.5, mm * 64.0) + 30.0;
+            }
+            if (d != S || cost >= best) continue;
+            best = cost; bestcode = code; bestn = np;
+        }
+    }
+    int c = bestcode, d = 0;
+    for (int i = 0; i < bestn; ++i) { const int len = 1 + c % 4; c /= 4; pd0[i] = d; pd1[i] = d + len - 1; d += len; }
+    *npass = bestn;
+}
+
 size_t ozaki_workspace_bytes(int n, int m, int S) {
-    const size_t nblk = (n + OZ_T - 1) / OZ_T, nk = (m + OZ_KS - 1) / OZ_KS;
-    return nblk * nk * (size_t)S * OZ_UNIT + 2 * (size_t)n * sizeof(double) + 256;
+    const size_t nblk = (n + OZ_T - 1) / OZ_T, nk = std::max(1, (m + OZ_KS - 1) / OZ_KS);
+    return nblk * nk * (size_t)S * OZ_UNIT + 2 * (size_t)n * sizeof(double) + nblk * (nblk + 1) / 2 * sizeof(unsigned int) + 1024;
 }
 
 // C(lower) = A' diag(d)^2 A + beta * D.  A: m x n (lda), d: m (or nullptr).  work: ozaki_workspace_bytes.
@@ -341,17 +453,36 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
         attr = true;
     }
     const int nblk = (n + OZ_T - 1) / OZ_T, nk = std::max(1, (m + OZ_KS - 1) / OZ_KS);
+    if (nblk > 65535) { set_error("ozaki_syrk: n too large"); return CVXB_E_ARG; }
+    const long long tiles = (long long)nblk * (nblk + 1) / 2;
     double *cs = reinterpret_cast<double *>(work);
     double *sinv = cs + n;
-    uint8_t *Q = reinterpret_cast<uint8_t *>(((uintptr_t)(sinv + n) + 255) & ~uintptr_t(255));
+    unsigned int *dtiles = reinterpret_cast<unsigned int *>(sinv + n);
+    uint8_t *Q = reinterpret_cast<uint8_t *>(((uintptr_t)(dtiles + tiles) + 255) & ~uintptr_t(255));
+    // launch order: bands of tile rows, column by column inside a band, so that the ~148 tiles in
+    // flight form a compact block (few distinct operand streams -> L2 hits instead of HBM reads)
+    static std::vector<unsigned int> order;
+    static int order_nblk = -1, order_band = -1;
+    int band = 12;
+    if (const char *e = getenv("CVXB_OZ_BAND")) band = std::max(1, atoi(e));
+    if (order_nblk != nblk || order_band != band) {
+        order.clear();
+        for (int r0 = 0; r0 < nblk; r0 += band) {
+            const int r1 = std::min(nblk, r0 + band);
+            for (int J = 0; J < r1; ++J)
+                for (int I = std::max(r0, J); I < r1; ++I) order.push_back(((unsigned)I << 16) | (unsigned)J);
+        }
+        order_nblk = nblk; order_band = band;
+    }
+    CVXB_CUDA(cudaMemcpyAsync(dtiles, order.data(), (size_t)tiles * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
     oz_colscale_kernel<<<n, 256, 0, st>>>(m, n, A, lda, d, cs, sinv);
     count_launch();
     oz_slice_kernel<<<dim3(nk, nblk), OZ_T, 0, st>>>(m, n, A, lda, d, sinv, Q, nk, S, layout);
     count_launch();
     OzParams p;
     p.Q = Q; p.cs = cs; p.D = D; p.ldd = ldd; p.C = C; p.ldc = ldc; p.beta = beta;
-    p.n = n; p.nblk = nblk; p.nk = nk; p.S = S; p.layout = layout; p.dbg = dbg;
-    const long long tiles = (long long)nblk * (nblk + 1) / 2;
+    p.n = n; p.nblk = nblk; p.nk = nk; p.S = S; p.layout = layout; p.dbg = dbg; p.tiles = dtiles;
+    oz_choose_groups(S, &p.npass, p.pd0, p.pd1);
     oz_mma_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM, st>>>(p);
     count_launch();
     CVXB_LAUNCH_CHECK();

@@ -151,9 +151,10 @@ int cvxb_max_step(double *x, const cvxb_dims *dims, double *sigma, double *resul
  * lapack.potrf lapack.c:1471; lapack.potrs lapack.c:1553. */
 int cvxb_syrk_scaled(int n, int k, const double *A, int lda, const double *rowscale,
                      const double *H, int ldh, double *C, int ldc, int device);
-/* EXPERIMENTAL (off the product path): the same SYRK, C(lower) = A' diag(d)^2 A + H, computed on the
- * int8 tensor path by error-free slicing (Ozaki scheme, `slices` = 1..9 radix-2^7 digits per entry;
- * 9 reproduces fp64).  Note d, not d^2 as in cvxb_syrk_scaled.  blas.syrk blas.c:3039. */
+/* The same SYRK, C(lower) = A' diag(d)^2 A + H, computed on the int8 tensor path by error-free
+ * slicing (Ozaki scheme, `slices` = 1..9 radix-2^7 digits per entry; 9 reproduces fp64).  Note d, not
+ * d^2 as in cvxb_syrk_scaled.  cvxb_kkt_factor uses it for large 'l' blocks (CVXB_OZAKI=0 disables).
+ * blas.syrk blas.c:3039. */
 int cvxb_syrk_scaled_i8(int n, int k, const double *A, int lda, const double *d, const double *H,
                         int ldh, double *C, int ldc, int slices, int device);
 /* work_inv: 2 * ceil(n/128) * 128*128 doubles — receives the inverses (and their

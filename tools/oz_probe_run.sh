@@ -1,19 +1,15 @@
 #!/bin/bash
-# bring-up sequence for the int8-slice SYRK: find the operand layout the MMA accepts, then accuracy + timing
+# int8-slice SYRK: correctness at several shapes, then timing of the level-group variants
 cd "$(dirname "$0")/.."
-OK=""
-for L in 0 1 2; do
-  echo "== layout $L"
-  timeout 40 tools/oz_probe onehot $L; r1=$?
-  timeout 40 tools/oz_probe ints $L 256 96; r2=$?
-  echo "   rc onehot=$r1 ints=$r2"
-  if [ $r1 -eq 0 ] && [ $r2 -eq 0 ] && [ -z "$OK" ]; then OK=$L; fi
+mkdir -p gpurun_out
+timeout 40 tools/oz_probe onehot 0
+timeout 60 tools/oz_probe full 0 300 200 9
+timeout 60 tools/oz_probe full 0 640 40000 9
+timeout 60 tools/oz_probe full 0 517 333 8
+echo "== default groups"
+timeout 120 tools/oz_probe perf 0 8192 16384 9 3
+for G in 2,3,4 2,4,3 4,4,1; do
+  echo "== groups $G"
+  CVXB_OZ_GROUPS=$G timeout 120 tools/oz_probe perf 0 8192 16384 9 2 | grep -E "rep|FAIL"
 done
-echo "== chosen layout: '$OK'"
-if [ -n "$OK" ]; then
-  timeout 60 tools/oz_probe full $OK 300 200 9
-  timeout 60 tools/oz_probe full $OK 1000 4100 9
-  timeout 60 tools/oz_probe full $OK 640 40000 9
-  timeout 120 tools/oz_probe perf $OK 8192 16384 9 3
-  timeout 120 tools/oz_probe perf $OK 8192 16384 8 2
-fi
+echo "== n=4096 m=8192"; timeout 120 tools/oz_probe perf 0 4096 8192 9 2 | grep -E "rep|PASS|FAIL"
