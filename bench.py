@@ -382,9 +382,9 @@ def main():
                         "peak_source": "nominal dense int8 rate of B200 (4.5 POP/s; MEASURED_PEAKS.json has no int8 entry); "
                                        "`achieved` counts int8 multiply-add ops of the 45 slice products",
                         "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
-                        # dram read + write of one launch from the ncu capture of the first version of the
-                        # kernel (same operand streams; profiles/r01k_ozaki_syrk_ncu_summary.md), n=8192 only
-                        "traffic": (14.40e9 + 0.80e9) if (n == 8192 and m == 16384) else None,
+                        # dram__bytes_read.sum + dram__bytes_write.sum of one oz_mma_kernel launch from the
+                        # committed ncu capture (profiles/r01k_ozaki_syrk_ncu_summary.md), n=8192 only
+                        "traffic": (17.30e9 + 0.81e9) if (n == 8192 and m == 16384) else None,
                         "algorithmic_bytes": 8.0 * m * n + 9.0 * m * n * 2 + 8.0 * n * n}
         else:
             roofline = {"kernel": "dmma_gemm_kernel<XK,YK,VEC> (fused NT-scaled SYRK)", "bound": "tensor",
