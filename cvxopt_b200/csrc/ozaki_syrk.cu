@@ -339,7 +339,11 @@ __global__ void oz_colscale_kernel(int m, int n, const double *A, long long lda,
     const int j = blockIdx.x;
     const double *a = A + (size_t)j * lda;
     double mx = 0.0;
-    for (int k = threadIdx.x; k < m; k += blockDim.x) mx = fmax(mx, fabs((d ? d[k] : 1.0) * a[k]));
+    for (int k = threadIdx.x; k < m; k += blockDim.x) {
+        double v = fabs((d ? d[k] : 1.0) * a[k]);
+        if (!(v <= 1.7976931348623157e308)) v = INFINITY;      // NaN or Inf entry: poison the column (below)
+        mx = fmax(mx, v);
+    }
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
     __syncthreads();
@@ -347,8 +351,9 @@ __global__ void oz_colscale_kernel(int m, int n, const double *A, long long lda,
         for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmax(mx, sh[w]);
         int e = 0;
         if (mx > 0.0 && mx < INFINITY) frexp(mx, &e);         // mx = f * 2^e, f in [0.5, 1): |x| < 2^e
-        cs[j] = ldexp(1.0, e);
-        sinv[j] = ldexp(64.0, -e);
+        // a non-finite entry makes row and column j of C NaN, as the fp64 kernel would (potrf then reports it)
+        cs[j] = (mx < INFINITY) ? ldexp(1.0, e) : __longlong_as_double(0x7ff8000000000000LL);
+        sinv[j] = (mx < INFINITY) ? ldexp(64.0, -e) : 0.0;
     }
 }
 
