@@ -160,7 +160,7 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     CVXB_TRY(check_device(device));
     cvxb_kkt *k = new cvxb_kkt();
     k->device = device; k->n = n; k->p = p;
-    if (const char *e = getenv("CVXB_OZAKI")) k->i8_mode = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
+    if (const char *e = getenv("CVXB_OZAKI")) k->i8_mode = (e[0] == '0') ? 0 : (e[0] == '2') ? 2 : 1;
     int rc = k->cone.init(dims);
     if (rc) { delete k; return rc; }
     const ConeLayout &c = k->cone;
