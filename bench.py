@@ -405,7 +405,11 @@ def main():
                        "l2": "inputs larger than L2 (G = %.2f GB, K = %.2f GB)" % (8.0 * n * m / 1e9, 8.0 * n * n / 1e9),
                        "flops_per_step": f_it,
                        "syrk_path": ("9 int8 slices per entry on tcgen05.mma kind::i8 (exact int32 products, fp64 recombination)"
-                                     if i8_default else "fp64 DMMA")},
+                                     if i8_default else "fp64 DMMA"),
+                       "precision": ("fp64 results: the slice products are exact integers and 9 slices keep 62 bits below each "
+                                     "column maximum; error vs an 80-bit evaluation 4e-16 * sum|terms|, the fp64 dot-product level "
+                                     "(tests/test_i8_syrk_gpu.py, profiles/r01k); the all-fp64 path is timed as other_syrk_path")
+                                    if i8_default else "fp64 throughout"},
             "e2e": {"value": e2e_val, "unit": "GF/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
