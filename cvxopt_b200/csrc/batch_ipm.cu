@@ -277,8 +277,10 @@ struct cvxb_batch {
     bool loaded = false;
     int iters_run = 0;
     double solve_ms = 0;
-    // single large problem: SYRK on the int8 tensor path (ozaki_syrk.cu), same rule as cvxb_kkt_factor
-    int i8_mode = 1;             // CVXB_OZAKI=0 off, 1 (default) when B == 1, n >= 4096, m >= 8192, 2 whenever B == 1
+    // single large problem: SYRK on the int8 tensor path (ozaki_syrk.cu).  Opt-in here (CVXB_OZAKI_IPM=1: when
+    // B == 1, n >= 4096, m >= 8192; =2: whenever B == 1): wired after the round-1 GPU budget was spent, so unlike
+    // cvxb_kkt_factor's use of the same kernel this call site has not run on a GPU yet.
+    int i8_mode = 0;
     void *oz_work = nullptr;
     size_t oz_bytes = 0;
 };
@@ -357,7 +359,7 @@ int cvxb_batch_create(cvxb_batch **out, int nprob, int n, int m, int device) {
     CVXB_CUDA(cudaSetDevice(device));
     cvxb_batch *b = new cvxb_batch();
     b->device = device; b->B = nprob; b->n = n; b->m = m;
-    if (const char *e = getenv("CVXB_OZAKI")) b->i8_mode = (e[0] == '0') ? 0 : (e[0] == '2') ? 2 : 1;
+    if (const char *e = getenv("CVXB_OZAKI_IPM")) b->i8_mode = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
     b->ldg = ((m + 1) & ~1) > 2 ? ((m + 1) & ~1) : 2;
     b->ldp = b->ldk = (n + 1) & ~1;
     b->sG = b->ldg * n; b->sP = b->ldp * n; b->sK = b->ldk * n;
