@@ -5,8 +5,16 @@ NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -X
 SRC := cvxopt_b200/csrc
 OBJ := $(SRC)/gemm_dmma.o $(SRC)/chol.o $(SRC)/cone.o $(SRC)/kkt_api.o $(SRC)/blocks_api.o $(SRC)/batch_ipm.o $(SRC)/cone_vec.o $(SRC)/ozaki_syrk.o
 LIB := cvxopt_b200/libcvxopt_b200.so
+# CPython extension mirroring cvxopt.misc_solvers over the C ABI (host side of the drop-in boundary)
+PYTHON ?= python
+PYINC := $(shell $(PYTHON) -c "import sysconfig; print(sysconfig.get_paths()['include'])")
+PYEXT := $(shell $(PYTHON) -c "import sysconfig; print(sysconfig.get_config_var('EXT_SUFFIX'))")
+EXT := cvxopt_b200/_misc_solvers$(PYEXT)
 
-all: $(LIB)
+all: $(LIB) $(EXT)
+
+$(EXT): $(SRC)/_misc_solvers.c include/cvxopt_b200.h $(LIB)
+	gcc -O2 -fPIC -shared -Wall -I$(PYINC) $< -o $@ -Lcvxopt_b200 -lcvxopt_b200 -Wl,-rpath,'$$ORIGIN'
 
 $(SRC)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/cone.cuh include/cvxopt_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -19,5 +27,11 @@ tools/oz_probe: tools/oz_probe.cu $(LIB)
 	$(NVCC) $(ARCH) -O2 -std=c++17 -cudart shared $< -o $@ -Lcvxopt_b200 -lcvxopt_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../cvxopt_b200'
 
 clean:
-	rm -f $(OBJ) $(LIB) tools/oz_probe
+	rm -f $(OBJ) $(LIB) $(EXT) tools/oz_probe
 .PHONY: all clean
+
+# roofline-denominator microbenchmarks (run on the GPU box; outputs are committed under profiles/)
+tools/int8_peak: tools/int8_peak.cu
+	$(NVCC) $(ARCH) -O2 -std=c++17 $< -o $@
+tools/fp64_peak: tools/fp64_peak.cu
+	$(NVCC) $(ARCH) -O2 -std=c++17 $< -o $@

@@ -31,8 +31,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "kkt_factor_solve_gflops_fp64"
-INT8_TENSOR_PEAK_TOPS = 4500.0      # nominal dense int8 (B200); no measured entry yet
-FP64_DMMA_PEAK_TFLOPS = 37.2   # tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peaks.md)
+INT8_TENSOR_NOMINAL_TOPS = 4500.0   # nominal dense int8 (B200): used only if no measured value is committed
+FP64_DMMA_PEAK_TFLOPS = 37.2   # tools/fp64_peak.cu on this pool's B200 (profiles/r01_fp64_peak_dmma_dfma.txt)
+
+
+def measured_constants():
+    """numbers measured on this pool's B200s by committed tools (tools/int8_peak.cu, ncu captures), kept in
+    profiles/measured_constants.json together with their sources"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "measured_constants.json")))
+    except Exception:       # noqa: BLE001
+        return {}
+
+
+def workload(n, m):
+    """the one workload string both arms print (config.workload)"""
+    return "dense QP KKT step n=%d m=%d ('l' cone): 1 factor + 2 solves (kkt_chol)" % (n, m)
 
 
 def flops(n, m, refinement=0):
@@ -81,28 +95,92 @@ def run_ipm(n, m, seed, device):
     it = int(r["iterations"][0])
     f_fac, f_sol, f_it = flops(n, m)
     return {"n": n, "m": m, "iterations": it, "status": r["status"][0], "ms_total": st["solve_ms"],
+            "syrk_path": st["syrk_path"],
             "wall_ms": wall, "iters_per_s": (it + 1) / (st["solve_ms"] * 1e-3),
             "primal_objective": float(r["primal objective"][0]),
             "gflops": (it + 1) * f_it / (st["solve_ms"] * 1e-3) * 1e-9}
 
 
-def run_batch(nprob, n, m, device, rank, world):
-    """BASELINE config 4: nprob independent QPs sharded over the ranks (contiguous blocks)"""
+def run_batch_distributed(nprob, n, m, rank, world, dev):
+    """BASELINE config 4 through cvxopt_b200.qp_batch_distributed: rank 0 holds every problem; timed region =
+    scatter (NCCL send/recv groups from rank 0's device copy) + solve + gather (NCCL), max over ranks."""
+    import torch
+    import torch.distributed as dist
     import cvxopt_b200
-    lo, hi = cvxopt_b200.shard_bounds(nprob, world)[rank]
-    Ps, qs, Gs, hs = [], [], [], []
-    for k in range(lo, hi):
-        P, q, G, h = make_qp(n, m, k)
-        Ps.append(P); qs.append(q); Gs.append(G); hs.append(h)
-    b = cvxopt_b200.QPBatch(hi - lo, n, m, device)
-    b.load(np.stack(Ps), np.stack(qs), np.stack(Gs), np.stack(hs))
-    b.solve()
-    b.solve()
-    r, st = b.results(), b.stats()
-    b.close()
-    return {"problems": hi - lo, "ms": st["solve_ms"], "lockstep_iterations": st["lockstep_iterations"],
-            "iterations_sum": int(r["iterations"].sum()),
-            "all_optimal": bool(all(x == "optimal" for x in r["status"]))}
+    args = (None, None, None, None)
+    if rank == 0:
+        P, q, G, h = (np.empty((nprob, n, n)), np.empty((nprob, n)), np.empty((nprob, m, n)), np.empty((nprob, m)))
+        for k in range(nprob):
+            P[k], q[k], G[k], h[k] = make_qp(n, m, k)
+        args = (P, q, G, h)
+    # warm-up on a small slice: NCCL point-to-point channels, kernels' first launches
+    warm = tuple(a[: 2 * world] for a in args) if rank == 0 else args
+    cvxopt_b200.qp_batch_distributed(*warm)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tm = {}
+    t0 = time.perf_counter()
+    res = cvxopt_b200.qp_batch_distributed(*args, timings=tm)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    keys = ("scatter_ms", "solve_ms", "gather_ms")
+    t = torch.tensor([tm[k] for k in keys] + [sum(tm[k] for k in keys), res.get("solve_ms", 0.0), wall],
+                     dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    full = res["all"]
+    total = float(t[3].item())
+    bf = flops(n, m)[2]
+    its = int(full["iterations"].sum())
+    return {"workload": "%d independent dense QPs n=%d m=%d held by rank 0: NCCL scatter -> device IPM on %d GPU(s) "
+                        "(interleaved shards) -> NCCL gather" % (nprob, n, m, world),
+            "scatter_ms": float(t[0].item()), "solve_ms": float(t[1].item()), "gather_ms": float(t[2].item()),
+            "ms": total, "ipm_kernel_ms": float(t[4].item()), "wall_ms_incl_h2d_of_batch": float(t[5].item()),
+            "timing": "device events per phase, max over ranks; ms = scatter + solve + gather; the one-off H2D of "
+                      "the 3.2 GB batch on rank 0 is outside (wall_ms includes it)",
+            "scattered_bytes": int(8 * (nprob - len(res["indices"])) * (n * n + n + m * n + m)),
+            "problems_per_s": nprob / (total * 1e-3), "ipm_iterations_total": its,
+            "gflops": (its + nprob) * bf / (total * 1e-3) * 1e-9,
+            "all_optimal": bool(all(x == "optimal" for x in full["status"])), "scaling": "strong"}
+
+
+def run_e2e_driver(n, m, seed, device):
+    """What a CVXOPT user sees: the UNMODIFIED reference driver solvers.qp (oracle/_ref acting as the host
+    application) at BASELINE config 2, (a) with this library's kktsolver and matrix-valued P, G (residual GEMVs
+    on the host), (b) with kktsolver + device-backed G/P operators.  Host Python glue included."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "cvxopt")):
+        return {"unavailable": "oracle/_ref not built"}
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import cvxopt_b200
+    from cvxopt import matrix, solvers
+    solvers.options["show_progress"] = False
+    P, q, G, h = make_qp(n, m, seed)
+    Pm, qm, Gm, hm = matrix(P), matrix(q), matrix(G), matrix(h)
+    dims = {"l": m, "q": [], "s": []}
+    f = cvxopt_b200.kkt_chol(Gm, dims, None, H=Pm, device=device)
+    out = {"workload": "solvers.coneqp dense QP n=%d m=%d through the unmodified reference driver" % (n, m)}
+
+    def Gop(u, v, alpha=1.0, beta=0.0, trans="N"):
+        f.G(u, v, alpha, beta, trans)
+
+    def Pop(u, v, alpha=1.0, beta=0.0):
+        f.P(u, v, alpha, beta)
+    for name, (Pa, Ga) in (("plugin", (Pm, Gm)), ("plugin_and_operators", (Pop, Gop))):
+        solvers.coneqp(Pa, qm, Ga, hm, dims, kktsolver=lambda W: f(W))         # warm-up
+        t0 = time.perf_counter()
+        sol = solvers.coneqp(Pa, qm, Ga, hm, dims, kktsolver=lambda W: f(W))
+        dt = time.perf_counter() - t0
+        out[name] = {"seconds": dt, "iterations": int(sol["iterations"]), "status": sol["status"],
+                     "ms_per_iteration": dt / (sol["iterations"] + 1) * 1e3,
+                     "iters_per_s": (sol["iterations"] + 1) / dt,
+                     "primal_objective": float(sol["primal objective"])}
+    f.close()
+    return out
 
 
 class ClockSampler:
@@ -154,7 +232,7 @@ def run_reference(args, rank, world):
     base = {"metric": METRIC, "unit": "GF/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "dense QP KKT step n=%d m=%d: 1 factor + 2 solves (kkt_chol)" % (n, m)}}
+            "config": {"workload": workload(n, m)}}
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
     if not os.path.isdir(os.path.join(ref_dir, "cvxopt")):
         base["unavailable"] = "oracle/_ref not built (oracle/build_ref.sh needs /root/reference)"
@@ -176,20 +254,28 @@ def run_reference(args, rank, world):
         for _ in range(2):
             x, z = matrix(rng.standard_normal(n)), matrix(rng.standard_normal(m))
             f(x, y, z)
-    # a full-size reference step takes tens of seconds on the host (single-threaded glue in
-    # misc.kkt_chol.factor): bound the sample so the whole arm ends within a few minutes
-    est = 2.4e-11 * f_it                      # ~ seconds per step at the ~45 GF/s measured on this pool
-    steps_run = max(1, min(args.steps, int(60.0 / max(est, 1e-3)) or 1))
-    warm_run = max(1, min(args.warmup, int(30.0 / max(est, 1e-3)) or 1))
-    for _ in range(warm_run):
+    # a full-size reference step takes 8-30 s on this pool's hosts (single-threaded glue in
+    # misc.kkt_chol.factor around the OpenBLAS calls): the number of timed steps is derived from the timed
+    # warm-up so that the whole arm ends within a few minutes, never fewer than 3
+    warm_run = 0
+    t0 = time.perf_counter()
+    step()
+    warm_run += 1
+    t_step = time.perf_counter() - t0
+    while warm_run < args.warmup and (warm_run + 1) * t_step < 20.0:
+        t0 = time.perf_counter()
         step()
+        t_step = min(t_step, time.perf_counter() - t0)
+        warm_run += 1
+    steps_run = max(3, min(args.steps, int(150.0 / max(t_step, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps_run):
         step()
     dt = time.perf_counter() - t0
     ms = dt / steps_run * 1e3
     val = f_it / (ms * 1e-3) * 1e-9
-    base.update({"value": val, "ms_per_step": ms,
+    base.update({"value": val, "ms_per_step": ms, "steps": steps_run, "warmup": warm_run,
+                 "steps_requested": args.steps, "warmup_requested": args.warmup,
                  "cpu_baseline": {"value": val, "unit": "GF/s", "cores": min(cores, 64), "kind": "reference",
                                   "sample": "%d full-size steps after %d warm-up (misc.kkt_chol, scipy-openblas)"
                                             % (steps_run, warm_run)},
@@ -259,6 +345,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ipm", action="store_true", help="skip the full-IPM and batch extras")
     ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--no-driver", action="store_true", help="skip the e2e_driver extra (solvers.coneqp n=4096)")
     ap.add_argument("--no-i8", action="store_true", help="skip the extra leg on the experimental int8-slice SYRK")
     args = ap.parse_args()
     if args.m <= 0:
@@ -376,15 +463,24 @@ def main():
             tiles = ((n + 127) // 128) * ((n + 127) // 128 + 1) // 2
             i8_ops = 45.0 * 2.0 * tiles * 128.0 * 128.0 * m
             a8 = i8_ops / (syrk * 1e-3) * 1e-12
+            mc = measured_constants()
+            pk = mc.get("int8_tensor_peak_tops")
+            peak8 = float(pk) if pk else INT8_TENSOR_NOMINAL_TOPS
+            tr = mc.get("oz_mma_dram_bytes_n8192_m16384") if (n == 8192 and m == 16384) else None
             roofline = {"kernel": "oz_mma_kernel (int8-slice SYRK: tcgen05.mma.kind::i8, int32 accumulators in TMEM)",
-                        "bound": "tensor", "achieved": a8, "peak": INT8_TENSOR_PEAK_TOPS, "unit": "TFLOP/s",
-                        "frac": a8 / INT8_TENSOR_PEAK_TOPS,
-                        "peak_source": "nominal dense int8 rate of B200 (4.5 POP/s; MEASURED_PEAKS.json has no int8 entry); "
-                                       "`achieved` counts int8 multiply-add ops of the 45 slice products",
+                        "bound": "tensor", "achieved": a8, "peak": peak8, "unit": "TFLOP/s",
+                        "frac": a8 / peak8,
+                        "peak_source": (mc.get("int8_tensor_peak_source") if pk else
+                                        "nominal dense int8 rate of B200 (4.5 POP/s): no measured value committed")
+                                       + "; `achieved` counts int8 multiply-add ops of the 45 slice products over "
+                                         "syrk_ms, which also covers the two slicing kernels",
+                        "nominal_int8_tops": INT8_TENSOR_NOMINAL_TOPS,
                         "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
-                        # dram__bytes_read.sum + dram__bytes_write.sum of one oz_mma_kernel launch from the
-                        # committed ncu capture (profiles/r01k_ozaki_syrk_ncu_summary.md), n=8192 only
-                        "traffic": (17.30e9 + 0.81e9) if (n == 8192 and m == 16384) else None,
+                        "fp64_equivalent_note": "above the fp64 DMMA peak only because it is a different pipe (int8 tensor)",
+                        # dram__bytes_read.sum + dram__bytes_write.sum of one oz_mma_kernel launch: from the committed
+                        # ncu capture named in profiles/measured_constants.json (not re-measured in this run)
+                        "traffic": float(tr) if tr else None,
+                        "traffic_source": mc.get("oz_mma_dram_source") if tr else None,
                         "algorithmic_bytes": 8.0 * m * n + 9.0 * m * n * 2 + 8.0 * n * n}
         else:
             roofline = {"kernel": "dmma_gemm_kernel<XK,YK,VEC> (fused NT-scaled SYRK)", "bound": "tensor",
@@ -394,13 +490,14 @@ def main():
                                        "MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 = 35.4)",
                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the
                         # committed capture profiles/r01j_syrk_band_order_dram.md (n=8192 only)
-                        "traffic": (7.30e9 + 0.275e9) if (n == 8192 and m == 16384) else None,
+                        "traffic": measured_constants().get("dmma_syrk_dram_bytes_n8192_m16384")
+                        if (n == 8192 and m == 16384) else None,
                         "algorithmic_bytes": 8.0 * m * n + 8.0 * n * n}
         out = {
             "metric": METRIC, "value": value, "unit": "GF/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "dense QP KKT step n=%d m=%d ('l' cone): 1 factor + 2 solves" % (n, m),
+            "config": {"workload": workload(n, m),
                        "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (G = %.2f GB, K = %.2f GB)" % (8.0 * n * m / 1e9, 8.0 * n * n / 1e9),
                        "flops_per_step": f_it,
@@ -465,31 +562,28 @@ def main():
     del kkt, d_d, d_di, xs, zs
     torch.cuda.empty_cache()
     if not args.no_ipm:
-        # config 4: batch of independent QPs, strong scaling over the ranks
-        bres = run_batch(args.batch, 512, 1024, local_rank, rank, world)
-        t = torch.tensor([bres["ms"]], dtype=torch.float64, device=dev)
-        cnt = torch.tensor([float(bres["iterations_sum"]), float(bres["problems"]), float(bres["all_optimal"])],
-                           dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            bf = flops(512, 1024)[2]
-            extras["batch"] = {"workload": "%d independent dense QPs n=512 m=1024, %d per GPU" % (args.batch, bres["problems"]),
-                               "ms": float(t.item()), "problems_per_s": args.batch / (float(t.item()) * 1e-3),
-                               "ipm_iterations_total": int(cnt[0].item()),
-                               "gflops": (cnt[0].item() + cnt[1].item()) * bf / (float(t.item()) * 1e-3) * 1e-9,
-                               "all_optimal": bool(cnt[2].item() == world), "scaling": "strong"}
-        # (ii) IPM iterations/s: a whole solve of the same-size QP, device resident (rank 0 only, last leg:
-        # nothing after it depends on it).  The device IPM's factor uses the fp64 DMMA SYRK (its int8-slice
-        # call site is opt-in, CVXB_OZAKI_IPM=1, until it has been validated on a GPU).
+        # config 4 (BASELINE): 512 independent dense QPs, ALL held by rank 0, through the path north_star names:
+        # NCCL scatter of the problem data -> device-resident lock-step IPM on every rank -> NCCL gather of the
+        # iterates (cvxopt_b200.qp_batch_distributed).  Strong scaling: total work fixed as N grows.
+        try:
+            extras_b = run_batch_distributed(args.batch, 512, 1024, rank, world, dev)
+            if rank == 0:
+                extras["batch"] = extras_b
+        except Exception as exc:            # noqa: BLE001  keep the headline line even if this extra leg fails
+            if rank == 0:
+                extras["batch"] = {"error": repr(exc)[:300]}
+        # (ii) IPM iterations/s: a whole solve of the same-size QP, device resident (rank 0 only).  The device
+        # IPM's factor takes the same SYRK path as `value` (int8 slices at this size; reported as syrk_path).
         if rank == 0:
             try:
-                ipm = run_ipm(n, m, args.seed, local_rank)
-                ipm["syrk_path"] = "int8 slices" if os.environ.get("CVXB_OZAKI_IPM", "0")[:1] in ("1", "2") else "fp64 DMMA"
-                extras["ipm"] = ipm
-            except Exception as exc:        # keep the headline line even if this extra leg fails
+                extras["ipm"] = run_ipm(n, m, args.seed, local_rank)
+            except Exception as exc:        # noqa: BLE001
                 extras["ipm"] = {"error": repr(exc)[:300]}
+            if world == 1 and not args.no_driver:
+                try:
+                    extras["e2e_driver"] = run_e2e_driver(4096, 8192, args.seed, local_rank)
+                except Exception as exc:    # noqa: BLE001
+                    extras["e2e_driver"] = {"error": repr(exc)[:300]}
     if rank == 0:
         out.update(extras)
         print(json.dumps(out))

@@ -51,7 +51,10 @@ _SIGS = {
     "cvxb_kkt_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
     "cvxb_kkt_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "cvxb_kkt_last_breakdown": (C.c_int, [C.c_void_p, c_double_p]),
+    "cvxb_kkt_syrk_path": (C.c_int, [C.c_void_p]),
     "cvxb_kkt_gemv_G": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                  C.c_int, C.c_int]),
+    "cvxb_kkt_gemv_A": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                   C.c_int, C.c_int]),
     "cvxb_kkt_symv_H": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                   C.c_int]),
@@ -82,6 +85,7 @@ _SIGS = {
                                   C.c_int]),
     "cvxb_batch_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]),
     "cvxb_batch_stats": (C.c_int, [C.c_void_p, c_double_p, c_int_p]),
+    "cvxb_batch_syrk_path": (C.c_int, [C.c_void_p]),
     "cvxb_batch_results": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
 }

@@ -84,7 +84,8 @@ class QPBatch:
     def stats(self):
         ms, it = C.c_double(), C.c_int()
         self._lib.cvxb_batch_stats(self._h, C.byref(ms), C.byref(it))
-        return {"solve_ms": ms.value, "lockstep_iterations": it.value}
+        return {"solve_ms": ms.value, "lockstep_iterations": it.value,
+                "syrk_path": ("none", "dmma", "int8")[self._lib.cvxb_batch_syrk_path(self._h)]}
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -115,7 +116,10 @@ def qp_batch(P, q, G, h, device=0, **options):
 
 # ---------------------------------------------------------------------------------------
 # multi-GPU: problems are independent -> shard them across ranks, no data-path collective.
-# One scatter of (P, q, G, h) from rank 0, one gather of (x, s, z, status, iters, objectives).
+# One scatter of (P, q, G, h) from rank 0, one gather of (x, s, z, status, iters, objectives):
+# point-to-point send/recv groups over the process group (NCCL over NVLink on GPUs: ncclSend/ncclRecv
+# inside one group call; gloo in the CPU tests), exact shard sizes, nothing padded, and on GPUs nothing
+# bounces through the host: shards land in device memory and QPBatch loads them from there.
 
 def shard_bounds(nprob, world):
     """contiguous block partition: rank r owns [lo, hi)"""
@@ -128,64 +132,176 @@ def shard_bounds(nprob, world):
     return bounds
 
 
-def qp_batch_distributed(P, q, G, h, solver=None, group=None, **options):
-    """Rank 0 passes the full batch (other ranks pass None); every rank returns its shard's
-    results and rank 0 additionally gets the gathered batch under key 'all'.
+def shard_indices(nprob, world, mode="interleaved"):
+    """problem indices owned by each rank.  'interleaved': i -> rank i mod world (spreads
+    hard and easy problems evenly, which matters because a rank's lock-step loop runs until its slowest
+    problem is done); 'contiguous': blocks (shard_bounds)."""
+    if mode == "contiguous":
+        return [np.arange(lo, hi) for lo, hi in shard_bounds(nprob, world)]
+    return [np.arange(r, nprob, world) for r in range(world)]
 
-    Collectives: scatter_object-free — plain tensor scatter/gather over the process group
-    (NCCL over NVLink on GPUs; gloo in the CPU tests, where `solver` is a stand-in)."""
+
+def _p2p(ops):
+    import torch.distributed as dist
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interleaved", timings=None,
+                         **options):
+    """Rank 0 passes the full batch (other ranks pass None); every rank returns its shard's results and
+    rank 0 additionally gets the gathered batch, in the original problem order, under key 'all'.
+
+    `timings` (dict, optional) receives scatter_ms / solve_ms / gather_ms of this rank, measured with
+    device events on the current stream (wall clock on CPU)."""
+    import time
     import torch
     import torch.distributed as dist
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+    else:                                   # no process group: a one-rank "world", same code path
+        rank, world, on_gpu = 0, 1, torch.cuda.is_available()
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    f64 = torch.float64
+
+    class _Clock:
+        def __init__(self):
+            self.t = {}
+            self._open = None
+
+        def start(self, name):
+            if on_gpu:
+                e = torch.cuda.Event(enable_timing=True); e.record()
+            else:
+                e = time.perf_counter()
+            self._open = (name, e)
+
+        def stop(self):
+            name, e0 = self._open
+            if on_gpu:
+                e1 = torch.cuda.Event(enable_timing=True); e1.record(); e1.synchronize()
+                self.t[name] = e0.elapsed_time(e1)
+            else:
+                self.t[name] = (time.perf_counter() - e0) * 1e3
+    clk = _Clock()
+
     meta = torch.zeros(3, dtype=torch.int64, device=dev)
+    full = None
     if rank == 0:
-        P, q, G, h = (np.asarray(a, dtype=np.float64) for a in (P, q, G, h))
-        meta = torch.tensor([P.shape[0], P.shape[1], G.shape[1]], dtype=torch.int64, device=dev)
-    dist.broadcast(meta, 0, group=group)
+        # the batch in the layout QPBatch loads: column-major n x n / m x n per problem
+        Pcm, qh, Gcm, hh, Btot, n, m = _stack(P, q, G, h)
+        meta = torch.tensor([Btot, n, m], dtype=torch.int64, device=dev)
+        full = [torch.from_numpy(a).to(dev) for a in (Pcm, qh, Gcm, hh)]       # one H2D of the whole batch
+    if world > 1:
+        dist.broadcast(meta, 0, group=group)
     Btot, n, m = (int(v) for v in meta.tolist())
-    bounds = shard_bounds(Btot, world)
-    lo, hi = bounds[rank]
-    cap = max(b[1] - b[0] for b in bounds)            # equal-sized scatter slots (padded)
+    owners = shard_indices(Btot, world, sharding)
+    mine = owners[rank]
+    k = len(mine)
+    tails = [(n, n), (n,), (n, m), (m,)]
 
-    def scatter(full, tail):
-        out = torch.zeros((cap,) + tail, dtype=torch.float64, device=dev)
-        if rank == 0:
-            chunks = []
-            for (a, b) in bounds:
-                c = torch.zeros((cap,) + tail, dtype=torch.float64)
-                c[: b - a] = torch.from_numpy(np.ascontiguousarray(full[a:b]))
-                chunks.append(c.to(dev))
-            dist.scatter(out, chunks, src=0, group=group)
-        else:
-            dist.scatter(out, None, src=0, group=group)
-        return out[: hi - lo].cpu().numpy()
-    Ps, qs, Gs, hs = scatter(P, (n, n)), scatter(q, (n,)), scatter(G, (m, n)), scatter(h, (m,))
-    if solver is None:
-        local_dev = torch.cuda.current_device() if backend == "nccl" else 0
-        solver = lambda a, b_, c, d: qp_batch(a, b_, c, d, device=local_dev, **options)   # noqa: E731
-    res = solver(Ps, qs, Gs, hs) if hi > lo else {
-        "x": np.zeros((0, n)), "s": np.zeros((0, m)), "z": np.zeros((0, m)),
-        "status_code": np.zeros(0, np.int32), "iterations": np.zeros(0, np.int32),
-        "primal objective": np.zeros(0), "dual objective": np.zeros(0)}
-
-    def gather(local, tail, dtype=torch.float64):
-        buf = torch.zeros((cap,) + tail, dtype=dtype, device=dev)
-        buf[: hi - lo] = torch.from_numpy(np.ascontiguousarray(local)).to(dtype).to(dev)
-        if rank == 0:
-            outs = [torch.zeros_like(buf) for _ in range(world)]
-            dist.gather(buf, outs, dst=0, group=group)
-            return np.concatenate([o[: b - a].cpu().numpy() for o, (a, b) in zip(outs, bounds)])
-        dist.gather(buf, None, dst=0, group=group)
-        return None
-    full = {"x": gather(res["x"], (n,)), "s": gather(res["s"], (m,)), "z": gather(res["z"], (m,)),
-            "status_code": gather(res["status_code"], (), torch.int64),
-            "iterations": gather(res["iterations"], (), torch.int64),
-            "primal objective": gather(res["primal objective"], ()),
-            "dual objective": gather(res["dual objective"], ())}
+    # ---- scatter ----
+    if on_gpu:
+        torch.cuda.synchronize()
+    clk.start("scatter_ms")
     if rank == 0:
-        full["status"] = [STATUS[int(k)] for k in full["status_code"]]
-        res = dict(res)
-        res["all"] = full
+        ops, keep = [], []
+        shard = None
+        for r in range(world):
+            idx = torch.from_numpy(owners[r]).to(dev)
+            parts = [t.index_select(0, idx) for t in full]            # contiguous copy of rank r's problems
+            if r == 0:
+                shard = parts
+            elif len(owners[r]):
+                keep.append(parts)
+                ops += [dist.P2POp(dist.isend, t, r, group) for t in parts]
+        _p2p(ops)
+        del keep, full
+    else:
+        shard = [torch.empty((k,) + t, dtype=f64, device=dev) for t in tails]
+        if k:
+            _p2p([dist.P2POp(dist.irecv, t, 0, group) for t in shard])
+    clk.stop()
+
+    # ---- solve ----
+    clk.start("solve_ms")
+    local_dev = torch.cuda.current_device() if on_gpu else 0
+    if solver is not None:
+        # stand-in (CPU tests): numpy in the public (B, m, n) layout
+        Pn, qn, Gn, hn = (t.cpu().numpy() for t in shard)
+        res = solver(np.transpose(Pn, (0, 2, 1)), qn, np.transpose(Gn, (0, 2, 1)), hn) if k else None
+        xs, ss, zs = ((torch.from_numpy(np.ascontiguousarray(res[key])).to(dev) if k
+                       else torch.empty((0, d), dtype=f64, device=dev)) for key, d in (("x", n), ("s", m), ("z", m)))
+        sc = torch.zeros((k, 4), dtype=f64, device=dev)
+        if k:
+            for j, key in enumerate(("status_code", "iterations", "primal objective", "dual objective")):
+                sc[:, j] = torch.from_numpy(np.asarray(res[key], dtype=np.float64))
+        stats = {}
+    else:
+        xs = torch.empty((k, n), dtype=f64, device=dev)
+        ss = torch.empty((k, m), dtype=f64, device=dev)
+        zs = torch.empty((k, m), dtype=f64, device=dev)
+        sc = torch.zeros((k, 4), dtype=f64, device=dev)
+        stats = {}
+        if k:
+            b = QPBatch(k, n, m, local_dev)
+            try:
+                # shards are already in device memory: straight into the batch, no host bounce
+                b.load_ptr(shard[0].data_ptr(), shard[1].data_ptr(), shard[2].data_ptr(), shard[3].data_ptr(),
+                           _lib.DEVICE)
+                b.solve(**options)
+                status = np.zeros(k, dtype=np.int32); iters = np.zeros(k, dtype=np.int32)
+                pobj, dobj = np.zeros(k), np.zeros(k)
+                lib = b._lib
+                _lib.check(lib.cvxb_batch_results(b._h, xs.data_ptr(), ss.data_ptr(), zs.data_ptr(), None, None,
+                                                  None, None, _lib.DEVICE), "batch_results")
+                _lib.check(lib.cvxb_batch_results(b._h, None, None, None, status.ctypes.data, iters.ctypes.data,
+                                                  pobj.ctypes.data, dobj.ctypes.data, _lib.HOST), "batch_results")
+                sc = torch.from_numpy(np.stack([status.astype(np.float64), iters.astype(np.float64), pobj, dobj],
+                                               axis=1)).to(dev)
+                stats = b.stats()
+            finally:
+                b.close()
+    del shard
+    clk.stop()
+
+    # ---- gather ----
+    clk.start("gather_ms")
+    local = [xs, ss, zs, sc]
+    gathered = None
+    if rank == 0:
+        outs = [torch.empty((Btot, d), dtype=f64, device=dev) for d in (n, m, m, 4)]
+        ops, bufs = [], {}
+        for r in range(1, world):
+            kr = len(owners[r])
+            if kr:
+                bufs[r] = [torch.empty((kr, d), dtype=f64, device=dev) for d in (n, m, m, 4)]
+                ops += [dist.P2POp(dist.irecv, t, r, group) for t in bufs[r]]
+        _p2p(ops)
+        bufs[0] = local
+        for r, parts in bufs.items():
+            idx = torch.from_numpy(owners[r]).to(dev)
+            for o, t in zip(outs, parts):
+                o.index_copy_(0, idx, t)
+        gathered = [o.cpu().numpy() for o in outs]
+    elif k:
+        _p2p([dist.P2POp(dist.isend, t, 0, group) for t in local])
+    clk.stop()
+    if timings is not None:
+        timings.update(clk.t)
+
+    scn = sc.cpu().numpy()
+    res = {"x": xs.cpu().numpy(), "s": ss.cpu().numpy(), "z": zs.cpu().numpy(),
+           "status_code": scn[:, 0].astype(np.int32), "iterations": scn[:, 1].astype(np.int32),
+           "primal objective": scn[:, 2].copy(), "dual objective": scn[:, 3].copy(), "indices": mine}
+    res.update(stats)
+    res["status"] = [STATUS[int(c)] for c in res["status_code"]]
+    if rank == 0:
+        g = gathered
+        res["all"] = {"x": g[0], "s": g[1], "z": g[2], "status_code": g[3][:, 0].astype(np.int64),
+                      "iterations": g[3][:, 1].astype(np.int64), "primal objective": g[3][:, 2].copy(),
+                      "dual objective": g[3][:, 3].copy(),
+                      "status": [STATUS[int(c)] for c in g[3][:, 0]]}
     return res

@@ -277,10 +277,11 @@ struct cvxb_batch {
     bool loaded = false;
     int iters_run = 0;
     double solve_ms = 0;
-    // single large problem: SYRK on the int8 tensor path (ozaki_syrk.cu).  Opt-in here (CVXB_OZAKI_IPM=1: when
-    // B == 1, n >= 4096, m >= 8192; =2: whenever B == 1): wired after the round-1 GPU budget was spent, so unlike
-    // cvxb_kkt_factor's use of the same kernel this call site has not run on a GPU yet.
-    int i8_mode = 0;
+    // single large problem: SYRK on the int8 tensor path (ozaki_syrk.cu), same rule as cvxb_kkt_factor:
+    // mode 1 (default) when B == 1, n >= 4096, m >= 8192; 2: whenever B == 1; 0: never.  CVXB_OZAKI (or the
+    // older CVXB_OZAKI_IPM) = 0/1/2 read at create.
+    int i8_mode = 1;
+    int syrk_path = 0;
     void *oz_work = nullptr;
     size_t oz_bytes = 0;
 };
@@ -289,19 +290,25 @@ namespace {
 
 int batch_factor(cvxb_batch *b) {
     cudaStream_t st = b->st;
-    if (b->B == 1 && b->m > 0 && (b->i8_mode == 2 || (b->i8_mode == 1 && b->n >= 4096 && b->m >= 8192))) {
-        // K = P + G' diag(di)^2 G from nine int8 slices per entry (fp64-accurate, ~1.8x the DMMA SYRK)
+    bool i8 = b->B == 1 && b->m > 0 && (b->i8_mode == 2 || (b->i8_mode == 1 && b->n >= 4096 && b->m >= 8192));
+    if (i8) {
+        // K = P + G' diag(di)^2 G from nine int8 slices per entry (fp64-accurate, ~1.8x the DMMA SYRK);
+        // same size rule and same fallback (workspace does not fit -> DMMA kernel) as cvxb_kkt_factor
         const size_t need = ozaki_workspace_bytes(b->n, b->m, 9);
         if (need > b->oz_bytes) {
             if (b->oz_work) cudaFree(b->oz_work);
             b->oz_work = nullptr; b->oz_bytes = 0;
             if (cudaMalloc(&b->oz_work, need) != cudaSuccess) {
                 cudaGetLastError();
-                set_error("batch: out of device memory for the int8 slice workspace (%zu bytes)", need);
-                return CVXB_E_NOMEM;
+                b->oz_work = nullptr;
+                i8 = false;
+            } else {
+                b->oz_bytes = need;
             }
-            b->oz_bytes = need;
         }
+    }
+    b->syrk_path = i8 ? 2 : 1;
+    if (i8) {
         CVXB_TRY(ozaki_syrk(b->n, b->m, b->G, b->ldg, b->p.di, b->P, b->ldp, 1.0, b->K, b->ldk, 9, 0,
                             b->oz_work, nullptr, st));
         CVXB_TRY(potrf_lower(b->n, b->K, (int)b->ldk, b->inv, b->cw, st));
@@ -359,6 +366,7 @@ int cvxb_batch_create(cvxb_batch **out, int nprob, int n, int m, int device) {
     CVXB_CUDA(cudaSetDevice(device));
     cvxb_batch *b = new cvxb_batch();
     b->device = device; b->B = nprob; b->n = n; b->m = m;
+    if (const char *e = getenv("CVXB_OZAKI")) b->i8_mode = (e[0] == '0') ? 0 : (e[0] == '2') ? 2 : 1;
     if (const char *e = getenv("CVXB_OZAKI_IPM")) b->i8_mode = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
     b->ldg = ((m + 1) & ~1) > 2 ? ((m + 1) & ~1) : 2;
     b->ldp = b->ldk = (n + 1) & ~1;
@@ -527,6 +535,8 @@ int cvxb_batch_results(cvxb_batch *b, double *x, double *s, double *z, int *stat
     }
     return 0;
 }
+
+int cvxb_batch_syrk_path(cvxb_batch *b) { return b ? b->syrk_path : CVXB_E_ARG; }
 
 int cvxb_batch_stats(cvxb_batch *b, double *solve_ms, int *iterations) {
     if (!b) return CVXB_E_ARG;

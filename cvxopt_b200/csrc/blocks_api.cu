@@ -4,19 +4,31 @@
 // (src/C/misc_solvers.c:1155-1173) on flat buffers.
 #include "cone.cuh"
 #include <map>
+#include <mutex>
 
 using namespace cvxb;
 
 namespace {
 
+// One context (stream + Cholesky workspace) per device, shared by the stateless entry points of this
+// file.  Calls on the same device are serialised by the context's mutex (held until the entry point
+// returns), calls on different devices run concurrently; the map itself is guarded by g_ctx_mu.
 struct DevCtx {
     cudaStream_t st = nullptr;
     CholWork cw;
     bool ok = false;
+    std::mutex mu;
 };
 std::map<int, DevCtx> g_ctx;
+std::mutex g_ctx_mu;
 
-int get_ctx(int device, DevCtx **out) {
+struct CtxRef {
+    DevCtx *c = nullptr;
+    std::unique_lock<std::mutex> lk;
+    DevCtx *operator->() const { return c; }
+};
+
+int get_ctx(int device, CtxRef *out) {
     int cnt = 0;
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
         cudaGetLastError();
@@ -25,13 +37,20 @@ int get_ctx(int device, DevCtx **out) {
     }
     if (device < 0 || device >= cnt) { set_error("device %d out of range", device); return CVXB_E_ARG; }
     CVXB_CUDA(cudaSetDevice(device));
-    DevCtx &c = g_ctx[device];
+    DevCtx *cp;
+    {
+        std::lock_guard<std::mutex> g(g_ctx_mu);
+        cp = &g_ctx[device];             // std::map nodes are address-stable
+    }
+    std::unique_lock<std::mutex> lk(cp->mu);
+    DevCtx &c = *cp;
     if (!c.ok) {
         CVXB_CUDA(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
         CVXB_TRY(chol_work_create(c.cw));
         c.ok = true;
     }
-    *out = &c;
+    out->c = cp;
+    out->lk = std::move(lk);
     return 0;
 }
 
@@ -70,7 +89,7 @@ extern "C" {
 
 int cvxb_syrk_scaled(int n, int k, const double *A, int lda, const double *rowscale,
                      const double *H, int ldh, double *C, int ldc, int device) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(device, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(device, &ctx));
     GemmDesc g;
     g.M = n; g.N = n; g.K = k;
     g.X = A; g.ldx = lda; g.x_kmajor = true;
@@ -85,7 +104,7 @@ int cvxb_syrk_scaled(int n, int k, const double *A, int lda, const double *rowsc
 
 int cvxb_syrk_scaled_i8(int n, int k, const double *A, int lda, const double *d, const double *H, int ldh,
                         double *C, int ldc, int slices, int device) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(device, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(device, &ctx));
     void *work = nullptr;
     if (slices < 1 || slices > 9) { set_error("syrk_scaled_i8: slices must be 1..9"); return CVXB_E_ARG; }
     if (cudaMalloc(&work, ozaki_workspace_bytes(n, k, slices)) != cudaSuccess) {
@@ -102,7 +121,7 @@ int cvxb_syrk_scaled_i8(int n, int k, const double *A, int lda, const double *d,
 }
 
 int cvxb_potrf(int n, double *A, int lda, double *work_inv, int device) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(device, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(device, &ctx));
     CVXB_TRY(potrf_lower(n, A, lda, work_inv, ctx->cw, ctx->st));
     int info = 0;
     CVXB_CUDA(cudaMemcpyAsync(&info, ctx->cw.d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
@@ -112,7 +131,7 @@ int cvxb_potrf(int n, double *A, int lda, double *work_inv, int device) {
 }
 
 int cvxb_potrs(int n, const double *L, int ldl, const double *inv, double *b, int device) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(device, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(device, &ctx));
     CVXB_TRY(potrs_lower(n, L, ldl, inv, b, ctx->cw, ctx->st));
     CVXB_CUDA(cudaStreamSynchronize(ctx->st));
     return 0;
@@ -120,7 +139,7 @@ int cvxb_potrs(int n, const double *L, int ldl, const double *inv, double *b, in
 
 int cvxb_gemm(int transa, int transb, int m, int n, int k, double alpha, const double *A, int lda,
               const double *B, int ldb, double beta, double *C, int ldc, int device) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(device, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(device, &ctx));
     const bool ta = (transa == 'T' || transa == 't'), tb = (transb == 'T' || transb == 't');
     GemmDesc g;
     g.M = m; g.N = n; g.K = k;
@@ -138,7 +157,7 @@ int cvxb_gemm(int transa, int transb, int m, int n, int k, double alpha, const d
 // ---------------------------------------------------------------- misc_solvers mirror
 int cvxb_scale(double *x, int xr, int xc, const cvxb_dims *dims, const cvxb_scaling *W, int trans,
                int inverse, int space) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(0, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(0, &ctx));
     cudaStream_t st = ctx->st;
     ConeLayout c;
     int rc = c.init(dims);
@@ -178,7 +197,7 @@ int cvxb_scale(double *x, int xr, int xc, const cvxb_dims *dims, const cvxb_scal
 }
 
 static int pack_common(const double *x, double *y, const cvxb_dims *dims, int space, bool do_pack) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(0, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(0, &ctx));
     cudaStream_t st = ctx->st;
     ConeLayout c;
     int rc = c.init(dims);
@@ -210,7 +229,7 @@ int cvxb_unpack(const double *x, double *y, const cvxb_dims *dims, int space) {
 }
 
 int cvxb_pack2(double *x, int xr, int xc, const cvxb_dims *dims, int space) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(0, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(0, &ctx));
     cudaStream_t st = ctx->st;
     ConeLayout c;
     int rc = c.init(dims);
@@ -238,7 +257,7 @@ int cvxb_pack2(double *x, int xr, int xc, const cvxb_dims *dims, int space) {
 }
 
 int cvxb_symm(double *x, int n, int space) {
-    DevCtx *ctx; CVXB_TRY(get_ctx(0, &ctx));
+    CtxRef ctx; CVXB_TRY(get_ctx(0, &ctx));
     Staged X;
     CVXB_TRY(X.in(x, (size_t)n * n, space, ctx->st));
     CVXB_TRY(symmetrize_lower(n, X.dev, n, 1, 0, ctx->st));

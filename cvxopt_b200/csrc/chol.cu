@@ -517,7 +517,7 @@ trsv_kernel(int n, const double *__restrict__ L, long long ldl, const double *__
     if (tid == 0) st_release(flags + bi, epoch);
 }
 
-int g_trsv_epoch = 0;
+std::atomic<int> g_trsv_epoch{0};   // flags written by an earlier launch never equal a later epoch
 
 }  // namespace
 
@@ -584,6 +584,9 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
     if (n <= 0) return 0;
     const int nblk = (n + NB - 1) / NB;
     if (w.panel_rows < n) {
+        // captured graphs bake in the panel addresses and their leading dimension: drop them
+        for (auto &g : w.graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        w.graphs.clear();
         for (int i = 0; i < 2; ++i) {
             if (w.panel[i]) CVXB_CUDA(cudaFree(w.panel[i]));
             w.panel[i] = nullptr;
@@ -736,7 +739,7 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
         return potrf_enqueue(n, A, lda, inv, w, st);
     }
     // second call with this key: capture
-    const unsigned long long l0 = g_launches;
+    const unsigned long long l0 = g_launches.load();
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
         cudaGetLastError();
         w.graph_failed = true;
@@ -745,8 +748,8 @@ int potrf_lower(int n, double *A, int lda, double *inv, CholWork &w, cudaStream_
     const int rc = potrf_enqueue(n, A, lda, inv, w, st);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    const int captured = (int)(g_launches - l0);
-    g_launches = l0;                                   // nothing has run yet
+    const int captured = (int)(g_launches.load() - l0);
+    g_launches.fetch_sub((unsigned long long)captured);    // nothing has run yet
     if (rc != 0 || ce != cudaSuccess || !graph) {
         cudaGetLastError();
         if (graph) cudaGraphDestroy(graph);
@@ -778,7 +781,7 @@ int trsv_lower(int n, const double *L, int ldl, const double *inv, double *b, bo
         CVXB_CUDA(cudaMalloc(&w.d_flags, (size_t)w.flags_cap * sizeof(int)));
         CVXB_CUDA(cudaMemset(w.d_flags, 0, (size_t)w.flags_cap * sizeof(int)));
     }
-    const int epoch = ++g_trsv_epoch;
+    const int epoch = g_trsv_epoch.fetch_add(1) + 1;
     const double *invT = inv + (long long)nblk * NB * NB;
     const bool vec = ((uintptr_t)L % 16 == 0) && (ldl % 2 == 0) && (batch == 1 || sL % 2 == 0);
     dim3 grid(nblk, batch);

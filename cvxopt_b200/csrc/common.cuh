@@ -6,14 +6,29 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <atomic>
 #include "../../include/cvxopt_b200.h"
 
 namespace cvxb {
 
 // ---- error plumbing ---------------------------------------------------------
 void set_error(const char *fmt, ...);
-extern unsigned long long g_launches;          // kernels launched by this library
-inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+extern std::atomic<unsigned long long> g_launches;   // kernels launched by this library
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// Function attributes (dynamic shared-memory opt-in ...) are PER DEVICE: a call site keeps one of
+// these and sets its attributes the first time it runs on each device of the process.
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    // returns the bit of the current device if its attributes are still to be set, else 0
+    unsigned long long pending() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        return (done.load(std::memory_order_acquire) & bit) ? 0ull : bit;
+    }
+    void mark(unsigned long long bit) { done.fetch_or(bit, std::memory_order_release); }
+};
 
 #define CVXB_CUDA(expr)                                                            \
     do {                                                                           \

@@ -101,9 +101,11 @@ namespace {
 
 __global__ void scale_rows_kernel(const double *src, long long lds, double *dst, long long ldd,
                                   int m, int xc, const double *w) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y;
-    if (i < m && j < xc) dst[i + j * ldd] = src[i + j * lds] * w[i];
+    // columns are strided over gridDim.y (capped at 65535 by the launch API; xc may exceed it)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double wi = w[i];
+    for (long long j = blockIdx.y; j < xc; j += gridDim.y) dst[i + j * ldd] = src[i + j * lds] * wi;
 }
 
 // one warp per (cone, column)
@@ -141,27 +143,27 @@ scale_q_kernel(const double *src, long long lds, double *dst, long long ldd, int
 }
 
 __global__ void pack_s_kernel(const double *src, long long lds, double *dst, long long ldd,
-                              const int *s, const int *soff, const int *spoff, int vector_mode) {
+                              const int *s, const int *soff, const int *spoff, int vector_mode, int xc) {
     const int k = blockIdx.z;
-    const long long j = blockIdx.y;
     const int ms = s[k];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ms * ms) return;
     const int i = e % ms, kk = e / ms;
     if (i < kk) return;
     const double sq2 = sqrt(2.0);
-    double x = src[soff[k] + e + j * lds];
-    double y;
-    if (i == kk) y = vector_mode ? (x / sq2) * sq2 : x;   // misc_solvers.c:454,462 vs :531-532
-    else y = x * sq2;
     const long long ip = (long long)kk * ms - (long long)kk * (kk - 1) / 2 + (i - kk);
-    dst[spoff[k] + ip + j * ldd] = y;
+    for (long long j = blockIdx.y; j < xc; j += gridDim.y) {
+        double x = src[soff[k] + e + j * lds];
+        double y;
+        if (i == kk) y = vector_mode ? (x / sq2) * sq2 : x;   // misc_solvers.c:454,462 vs :531-532
+        else y = x * sq2;
+        dst[spoff[k] + ip + j * ldd] = y;
+    }
 }
 
 __global__ void unpack_s_kernel(const double *src, long long lds, double *dst, long long ldd,
-                                const int *s, const int *soff, const int *spoff) {
+                                const int *s, const int *soff, const int *spoff, int xc) {
     const int k = blockIdx.z;
-    const long long j = blockIdx.y;
     const int ms = s[k];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ms * ms) return;
@@ -169,8 +171,10 @@ __global__ void unpack_s_kernel(const double *src, long long lds, double *dst, l
     if (i < kk) return;
     const double a = 1.0 / sqrt(2.0);                        // misc_solvers.c:556
     const long long ip = (long long)kk * ms - (long long)kk * (kk - 1) / 2 + (i - kk);
-    double x = src[spoff[k] + ip + j * lds];
-    dst[soff[k] + e + j * ldd] = (i == kk) ? x : x * a;
+    for (long long j = blockIdx.y; j < xc; j += gridDim.y) {
+        double x = src[spoff[k] + ip + j * lds];
+        dst[soff[k] + e + j * ldd] = (i == kk) ? x : x * a;
+    }
 }
 
 // dst (ms x ms full, batch stride ms*ms) = symmetric completion of the lower triangle of
@@ -343,7 +347,7 @@ __global__ void vec_axpby_kernel(int n, double alpha, const double *x, double be
 int scale_rows(const double *src, long long lds, double *dst, long long ldd, int m, int xc,
                const double *w, cudaStream_t st) {
     if (m <= 0 || xc <= 0) return 0;
-    dim3 grid((m + 255) / 256, xc);
+    dim3 grid((m + 255) / 256, xc < 65535 ? xc : 65535);
     scale_rows_kernel<<<grid, 256, 0, st>>>(src, lds, dst, ldd, m, xc, w);
     count_launch();
     CVXB_LAUNCH_CHECK();
@@ -364,9 +368,9 @@ int scale_q(const ConeLayout &c, const DevScaling &W, const double *src, long lo
 int pack_s(const ConeLayout &c, const double *src, long long lds, double *dst, long long ldd,
            int xc, bool vector_mode, cudaStream_t st) {
     if (c.ns == 0 || xc <= 0 || c.maxs == 0) return 0;
-    dim3 grid((c.maxs * c.maxs + 255) / 256, xc, c.ns);
+    dim3 grid((c.maxs * c.maxs + 255) / 256, xc < 65535 ? xc : 65535, c.ns);
     pack_s_kernel<<<grid, 256, 0, st>>>(src, lds, dst, ldd, c.d_s, c.d_soff, c.d_spoff,
-                                        vector_mode ? 1 : 0);
+                                        vector_mode ? 1 : 0, xc);
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;
@@ -375,8 +379,8 @@ int pack_s(const ConeLayout &c, const double *src, long long lds, double *dst, l
 int unpack_s(const ConeLayout &c, const double *src, long long lds, double *dst, long long ldd,
              int xc, cudaStream_t st) {
     if (c.ns == 0 || xc <= 0 || c.maxs == 0) return 0;
-    dim3 grid((c.maxs * c.maxs + 255) / 256, xc, c.ns);
-    unpack_s_kernel<<<grid, 256, 0, st>>>(src, lds, dst, ldd, c.d_s, c.d_soff, c.d_spoff);
+    dim3 grid((c.maxs * c.maxs + 255) / 256, xc < 65535 ? xc : 65535, c.ns);
+    unpack_s_kernel<<<grid, 256, 0, st>>>(src, lds, dst, ldd, c.d_s, c.d_soff, c.d_spoff, xc);
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;

@@ -7,6 +7,7 @@
 // plane rotations at once, one thread per 2x2 block of J'AJ, ping-ponging between two copies so a
 // round is a single race-free pass.
 #include "cone.cuh"
+#include <mutex>
 #include <map>
 #include <vector>
 #include <algorithm>
@@ -410,6 +411,8 @@ int vctx(cudaStream_t *st) {
         return CVXB_E_NOGPU;
     }
     CVXB_CUDA(cudaSetDevice(0));
+    static std::mutex mu;               // creation only; a CUDA stream itself may be shared by threads
+    std::lock_guard<std::mutex> g(mu);
     if (!g_v.ok) { CVXB_CUDA(cudaStreamCreateWithFlags(&g_v.st, cudaStreamNonBlocking)); g_v.ok = true; }
     *st = g_v.st;
     return 0;

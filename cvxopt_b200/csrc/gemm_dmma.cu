@@ -704,10 +704,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 
 // returns 0 on launch, 1 when this path does not apply (caller falls back to the cp.async kernel)
 int launch_syrk_tma(const KParams &p, int units, cudaStream_t st) {
-    static int state = 0;              // 0 untested, 1 usable, -1 unusable
-    static EncodeTiledFn encode = nullptr;
-    if (state == 0) {
-        state = -1;
+    static std::atomic<int> state{0};  // 0 untested, 1 usable, -1 unusable
+    static std::atomic<EncodeTiledFn> encode_fn{nullptr};
+    static DeviceOnce once;
+    if (state.load() == 0) {
+        int ns = -1;
         // opt-in (CVXB_TMA=1): parity-green, but measured 79-82 % DMMA utilisation against 89.5 % for
         // the cp.async kernel on the north-star SYRK (profiles/r01g_syrk_tma_ncu_summary.md)
         const char *on = getenv("CVXB_TMA");
@@ -716,15 +717,20 @@ int launch_syrk_tma(const KParams &p, int units, cudaStream_t st) {
             cudaDriverEntryPointQueryResult q;
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
                 q == cudaDriverEntryPointSuccess && fn) {
-                encode = reinterpret_cast<EncodeTiledFn>(fn);
-                if (cudaFuncSetAttribute(dmma_syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         T_SMEM) == cudaSuccess)
-                    state = 1;
+                encode_fn.store(reinterpret_cast<EncodeTiledFn>(fn));
+                ns = 1;
             }
             cudaGetLastError();
         }
+        state.store(ns);
     }
-    if (state != 1) return 1;
+    if (state.load() != 1) return 1;
+    if (const unsigned long long bit = once.pending()) {
+        if (cudaFuncSetAttribute(dmma_syrk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM) !=
+            cudaSuccess) { cudaGetLastError(); return 1; }
+        once.mark(bit);
+    }
+    const EncodeTiledFn encode = encode_fn.load();
     // the matrix as TMA sees it: dim0 = k (contiguous), dim1 = row/column index of C
     CUtensorMap mx, my;
     const cuuint64_t gdimx[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
@@ -749,13 +755,13 @@ int launch_syrk_tma(const KParams &p, int units, cudaStream_t st) {
 
 template <bool XK, bool YK, bool VEC>
 int launch_inst(const KParams &p, dim3 grid, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;              // per instantiation, per device
+    if (const unsigned long long bit = once.pending()) {
         CVXB_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<XK, YK, VEC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         CVXB_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<XK, YK, VEC>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+        once.mark(bit);
     }
     dmma_gemm_kernel<XK, YK, VEC><<<grid, THREADS, SMEM_BYTES, st>>>(p);
     count_launch();

@@ -13,7 +13,7 @@
 namespace cvxb {
 
 static thread_local std::string g_err;
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char *fmt, ...) {
     char buf[1024];
@@ -94,6 +94,7 @@ struct cvxb_kkt {
     int i8_mode = 1;
     void *oz_work = nullptr;
     size_t oz_bytes = 0;
+    int syrk_path = 0;           // kernel of the last factor's 'l'-row SYRK: 0 none, 1 fp64 DMMA, 2 int8 slices
 };
 
 namespace {
@@ -121,7 +122,7 @@ extern "C" {
 
 const char *cvxb_last_error(void) { return g_err.c_str(); }
 int cvxb_version(void) { return 100; }
-unsigned long long cvxb_launch_count(void) { return g_launches; }
+unsigned long long cvxb_launch_count(void) { return g_launches.load(); }
 
 int cvxb_device_count(void) {
     int cnt = 0;
@@ -231,6 +232,8 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     KCUDA(cudaMalloc(&k->yv, (cd > nn ? cd : nn) * sizeof(double)));
     {
         size_t w1 = cd * (size_t)gemv_n_chunks(n), w2 = nn * (size_t)gemv_n_chunks(p > 0 ? p : 1);
+        const size_t w3 = (size_t)(p > 0 ? p : 1) * (size_t)gemv_n_chunks(n);      // A operator
+        if (w3 > w1) w1 = w3;
         KCUDA(cudaMalloc(&k->gemv_ws, (w1 > w2 ? w1 : w2) * sizeof(double)));
     }
     KCUDA(cudaStreamSynchronize(k->st));
@@ -327,23 +330,30 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
     int info = 0;
     auto assemble_and_factor = [&](bool add_ata) -> int {
         bool have = false;
-        const bool i8 = k->i8_mode == 2 || (k->i8_mode == 1 && n >= 4096 && c.ml >= 8192);
+        bool i8 = k->i8_mode == 2 || (k->i8_mode == 1 && n >= 4096 && c.ml >= 8192);
         if (c.ml > 0 && n > 0 && i8) {
-            // G_l' diag(di)^2 G_l + H from nine int8 slices per entry (exact products, fp64-level result)
+            // the slice workspace is ~1.125 x sizeof(G_l): when it does not fit, the DMMA kernel (no
+            // workspace) computes the same K
             const size_t need = ozaki_workspace_bytes(n, c.ml, 9);
             if (need > k->oz_bytes) {
                 if (k->oz_work) cudaFree(k->oz_work);
                 k->oz_work = nullptr; k->oz_bytes = 0;
                 if (cudaMalloc(&k->oz_work, need) != cudaSuccess) {
                     cudaGetLastError();
-                    set_error("factor: out of device memory for the int8 slice workspace (%zu bytes)", need);
-                    return CVXB_E_NOMEM;
+                    k->oz_work = nullptr;
+                    i8 = false;
+                } else {
+                    k->oz_bytes = need;
                 }
-                k->oz_bytes = need;
             }
+        }
+        k->syrk_path = 0;
+        if (c.ml > 0 && n > 0 && i8) {
+            // G_l' diag(di)^2 G_l + H from nine int8 slices per entry (exact products, fp64-level result)
             CVXB_TRY(ozaki_syrk(n, c.ml, k->G + c.mnl, k->ldg, k->W.di, Hptr, ldH, 1.0, k->Kmat, ldk, 9, 0,
                                 k->oz_work, nullptr, st));
             have = true;
+            k->syrk_path = 2;
         } else if (c.ml > 0 && n > 0) {
             GemmDesc g;
             g.M = n; g.N = n; g.K = c.ml;
@@ -355,6 +365,7 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
             g.lower_only = true; g.splitk_ws = k->cw.splitk_ws;
             CVXB_TRY(dmma_gemm(g, st));
             have = true;
+            k->syrk_path = 1;
         }
         if (k->nrest > 0 && n > 0) {
             GemmDesc g;
@@ -567,6 +578,7 @@ int cvxb_kkt_trace(cvxb_kkt *k, unsigned long long *out, int nsteps) {
     CVXB_CUDA(cudaMemcpy(out, k->cw.trace, (size_t)nsteps * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
+int cvxb_kkt_syrk_path(cvxb_kkt *k) { return k ? k->syrk_path : CVXB_E_ARG; }
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3) {
     if (!k || !ms3) return CVXB_E_ARG;
     ms3[0] = k->br[1]; ms3[1] = k->br[2]; ms3[2] = k->br[0];
@@ -593,6 +605,31 @@ int cvxb_kkt_gemv_G(cvxb_kkt *k, const double *x, double *y, double alpha, doubl
     }
     if (tr) CVXB_TRY(gemv_t(m, n, Gp, k->ldg, nullptr, xd, alpha, beta, yd, st));
     else    CVXB_TRY(gemv_n(m, n, Gp, k->ldg, nullptr, xd, alpha, beta, yd, k->gemv_ws, st));
+    if (space != CVXB_DEVICE) CVXB_TRY(xfer_vec(y, yd, ny, CVXB_HOST, false, st));
+    CVXB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int cvxb_kkt_gemv_A(cvxb_kkt *k, const double *x, double *y, double alpha, double beta, int trans,
+                    int space) {
+    if (!k || !x || !y) { set_error("gemv_A: bad arguments"); return CVXB_E_ARG; }
+    if (k->p <= 0) { set_error("gemv_A: the factory was created without equality constraints"); return CVXB_E_ARG; }
+    CVXB_CUDA(cudaSetDevice(k->device));
+    const int n = k->n, p = k->p;
+    cudaStream_t st = k->st;
+    const bool tr = (trans == 'T' || trans == 't');
+    const int nx = tr ? p : n, ny = tr ? n : p;
+    const double *xd = x; double *yd = y;
+    if (space != CVXB_DEVICE) {
+        // xv (n) / yd (p) by role; yv is max(cdim, n) long and serves as the second n- or p-vector
+        double *xb = tr ? k->yd : k->xv, *yb = k->yv;
+        if (!tr && p > n) { set_error("gemv_A: p > n"); return CVXB_E_ARG; }
+        CVXB_TRY(xfer_vec(xb, x, nx, CVXB_HOST, true, st));
+        if (beta != 0.0) CVXB_TRY(xfer_vec(yb, y, ny, CVXB_HOST, true, st));
+        xd = xb; yd = yb;
+    }
+    if (tr) CVXB_TRY(gemv_t(p, n, k->Aeq, k->lda_eq, nullptr, xd, alpha, beta, yd, st));
+    else    CVXB_TRY(gemv_n(p, n, k->Aeq, k->lda_eq, nullptr, xd, alpha, beta, yd, k->gemv_ws, st));
     if (space != CVXB_DEVICE) CVXB_TRY(xfer_vec(y, yd, ny, CVXB_HOST, false, st));
     CVXB_CUDA(cudaStreamSynchronize(st));
     return 0;

@@ -452,10 +452,10 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
                cudaStream_t st) {
     if (n <= 0) return 0;
     if (S < 1 || S > OZ_SMAX || !A || !C || !work || m < 0) { set_error("ozaki_syrk: bad arguments"); return CVXB_E_ARG; }
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce once;
+    if (const unsigned long long bit = once.pending()) {
         CVXB_CUDA(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-        attr = true;
+        once.mark(bit);
     }
     const int nblk = (n + OZ_T - 1) / OZ_T, nk = std::max(1, (m + OZ_KS - 1) / OZ_KS);
     if (nblk > 65535) { set_error("ozaki_syrk: n too large"); return CVXB_E_ARG; }
@@ -466,18 +466,16 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     uint8_t *Q = reinterpret_cast<uint8_t *>(((uintptr_t)(dtiles + tiles) + 255) & ~uintptr_t(255));
     // launch order: bands of tile rows, column by column inside a band, so that the ~148 tiles in
     // flight form a compact block (few distinct operand streams -> L2 hits instead of HBM reads)
-    static std::vector<unsigned int> order;
-    static int order_nblk = -1, order_band = -1;
+    // (rebuilt per call: a few microseconds, and no shared mutable state between threads / handles; the
+    // pageable-source copy is staged before cudaMemcpyAsync returns)
+    std::vector<unsigned int> order;
+    order.reserve((size_t)tiles);
     int band = 12;
     if (const char *e = getenv("CVXB_OZ_BAND")) band = std::max(1, atoi(e));
-    if (order_nblk != nblk || order_band != band) {
-        order.clear();
-        for (int r0 = 0; r0 < nblk; r0 += band) {
-            const int r1 = std::min(nblk, r0 + band);
-            for (int J = 0; J < r1; ++J)
-                for (int I = std::max(r0, J); I < r1; ++I) order.push_back(((unsigned)I << 16) | (unsigned)J);
-        }
-        order_nblk = nblk; order_band = band;
+    for (int r0 = 0; r0 < nblk; r0 += band) {
+        const int r1 = std::min(nblk, r0 + band);
+        for (int J = 0; J < r1; ++J)
+            for (int I = std::max(r0, J); I < r1; ++I) order.push_back(((unsigned)I << 16) | (unsigned)J);
     }
     CVXB_CUDA(cudaMemcpyAsync(dtiles, order.data(), (size_t)tiles * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
     oz_colscale_kernel<<<n, 256, 0, st>>>(m, n, A, lda, d, cs, sinv);

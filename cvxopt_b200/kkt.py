@@ -209,6 +209,20 @@ class KKTChol:
                                        float(beta), ord(trans), _lib.HOST)
         _lib.check(rc, "G operator")
 
+    def A(self, x, y, alpha=1.0, beta=0.0, trans="N"):
+        """y := alpha*A*x + beta*y ('N') or alpha*A'*x + beta*y ('T') on the resident equality-constraint
+        matrix (function-valued A protocol, reference coneprog.py:1682-1711)."""
+        if not self.p:
+            raise ValueError("this factory was created without equality constraints")
+        nx, ny = (self.p, self.n) if trans == "T" else (self.n, self.p)
+        xv = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, order="F"))
+        yv = _vec_inplace(y, ny, "y")
+        if xv.size != nx:
+            raise TypeError("x must have %d entries" % nx)
+        rc = self._lib.cvxb_kkt_gemv_A(self._h, xv.ctypes.data, yv.ctypes.data, float(alpha),
+                                       float(beta), ord(trans), _lib.HOST)
+        _lib.check(rc, "A operator")
+
     def P(self, x, y, alpha=1.0, beta=0.0):
         """y := alpha*H*x + beta*y on the resident H (function-valued P protocol)."""
         xv = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1, order="F"))
@@ -249,6 +263,10 @@ class KKTChol:
         self._lib.cvxb_kkt_last_breakdown(self._h, b)
         return {"syrk_ms": b[0], "potrf_ms": b[1], "scale_ms": b[2]}
 
+    def syrk_path(self):
+        """'none' | 'dmma' | 'int8': the kernel that computed the last factor's 'l'-row SYRK"""
+        return ("none", "dmma", "int8")[self._lib.cvxb_kkt_syrk_path(self._h)]
+
     def get_L(self):
         L = np.zeros((self.n, self.n), order="F")
         _lib.check(self._lib.cvxb_kkt_get_L(self._h, L.ctypes.data, max(1, self.n)), "get_L")
@@ -274,6 +292,34 @@ def kkt_chol(G, dims, A=None, mnl=0, H=None, device=0):
     so `factor(W)` / `factor(W, P)` do not re-upload n^2 doubles per iteration.
     """
     return KKTChol(G, dims, A, mnl, H, device)
+
+
+def cpl_kktsolver(F, G, dims, A=None, mnl=0, device=0):
+    """`kktsolver(x, z, W)` for `cvxprog.cpl` backed by the device KKT path: what cpl builds itself for
+    kktsolver='chol' (reference cvxprog.py:526-537) with misc.kkt_chol replaced by this library:
+
+        factor = kkt_chol(G, dims, A, mnl);  kktsolver(x, z, W) = factor(W, H, Df)  with f, Df, H = F(x, z)
+
+    G is uploaded once; each call uploads the fresh dense H (n x n) and Df (mnl x n)."""
+    factor = KKTChol(G, dims, A, mnl, None, device)
+
+    def kktsolver(x, z, W):
+        f, Df, H = F(x, z)
+        return factor(W, H, Df)
+    kktsolver.factory = factor
+    return kktsolver
+
+
+def cp_kktsolver(F, G, dims, A=None, mnl=0, device=0):
+    """`kktsolver(x, z, W)` for `cvxprog.cp` (reference cvxprog.py:1876-1887): F's first row is the objective,
+    so the nonlinear constraint block is Df[1:, :] and `mnl` counts the nonlinear CONSTRAINTS only."""
+    factor = KKTChol(G, dims, A, mnl, None, device)
+
+    def kktsolver(x, z, W):
+        f, Df, H = F(x, z)
+        return factor(W, H, Df[1:, :])
+    kktsolver.factory = factor
+    return kktsolver
 
 
 def kkt_chol2(G, dims, A=None, mnl=0, H=None, device=0):

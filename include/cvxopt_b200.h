@@ -113,6 +113,10 @@ int cvxb_kkt_timer_stop(cvxb_kkt *k, double *ms);
 int cvxb_kkt_trace(cvxb_kkt *k, unsigned long long *out, int nsteps);
 /* per-kernel-class CUDA-event breakdown of the last factor (syrk, potrf, scale) */
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3);
+/* which kernel computed the 'l'-row SYRK of the last factor: 0 none (ml == 0), 1 fp64 DMMA
+ * (mma.sync.m8n8k4.f64), 2 int8 slices on tcgen05.mma kind::i8 (large problems; CVXB_OZAKI=0 disables,
+ * falls back to 1 when the slice workspace does not fit in device memory) */
+int cvxb_kkt_syrk_path(cvxb_kkt *k);
 
 /* device-resident G / P operators for the function-valued G(x,y,alpha,beta,trans)
  * / P(x,y,alpha,beta) protocol of coneprog (coneprog.py:1682-1711):
@@ -122,6 +126,10 @@ int cvxb_kkt_gemv_G(cvxb_kkt *k, const double *x, double *y, double alpha, doubl
                     int trans, int space);
 int cvxb_kkt_symv_H(cvxb_kkt *k, const double *x, double *y, double alpha, double beta,
                     int space);
+/* y := alpha*A*x + beta*y ('N') or alpha*A'*x + beta*y ('T') on the resident equality-constraint
+ * matrix: the function-valued A(x, y, alpha, beta, trans) protocol (coneprog.py:1682-1711) */
+int cvxb_kkt_gemv_A(cvxb_kkt *k, const double *x, double *y, double alpha, double beta,
+                    int trans, int space);
 
 /* ---- cone algebra: mirror of src/C/misc_solvers.c (12 entry points,
  * misc_solvers.c:1155-1173).  x is xr x xc column-major with leading
@@ -180,6 +188,8 @@ int cvxb_batch_results(cvxb_batch *b, double *x, double *s, double *z, int *stat
                        int *iters, double *pobj, double *dobj, int space);
 /* CUDA-event time of the last cvxb_batch_solve and the number of lock-step iterations run */
 int cvxb_batch_stats(cvxb_batch *b, double *solve_ms, int *iterations);
+/* kernel of the factorisations' SYRK in the last solve: 1 fp64 DMMA, 2 int8 slices (as cvxb_kkt_syrk_path) */
+int cvxb_batch_syrk_path(cvxb_batch *b);
 
 #ifdef __cplusplus
 }

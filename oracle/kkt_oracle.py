@@ -247,9 +247,12 @@ class KktChol:
         scale(Gs, W, trans="T", inverse="I")                         # :1271
         pack2(Gs, self.dims, mnl)                                    # :1272
         Gp = Gs[:self.cdim_pckd, :]
-        K = Gp.T @ Gp                                                # blas.syrk trans='T'  :1275
+        # blas.syrk(Gs, K, trans='T', k=cdim_pckd): lower triangle only  (:1275)
+        K = sla.blas.dsyrk(1.0, Gp, trans=1, lower=1) if Gp.shape[0] else np.zeros((n, n), order="F")
         if H is not None:
-            K = K + np.tril(np.asarray(H)) + np.tril(np.asarray(H), -1).T   # :1276-1277
+            K += np.tril(np.asarray(H))                              # K[:n,:n] += H  (:1276, lower part matters)
+        K = K + np.tril(K, -1).T                                     # misc.symm  (:1277)
+        self.K1norm = float(np.abs(K).sum(axis=0).max()) if n else 0.0    # for condition estimates in tests
         if self.A is not None and self.singular:
             K = K + self.A.T @ self.A
         try:
