@@ -202,6 +202,12 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
     k = len(mine)
     tails = [(n, n), (n,), (n, m), (m,)]
 
+    # ---- setup (not data path): this rank's batch object = its device allocations ----
+    local_dev = torch.cuda.current_device() if on_gpu else 0
+    clk.start("setup_ms")
+    bobj = QPBatch(k, n, m, local_dev) if (solver is None and k) else None
+    clk.stop()
+
     # ---- scatter ----
     if on_gpu:
         torch.cuda.synchronize()
@@ -227,7 +233,6 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
 
     # ---- solve ----
     clk.start("solve_ms")
-    local_dev = torch.cuda.current_device() if on_gpu else 0
     if solver is not None:
         # stand-in (CPU tests): numpy in the public (B, m, n) layout
         Pn, qn, Gn, hn = (t.cpu().numpy() for t in shard)
@@ -246,7 +251,7 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
         sc = torch.zeros((k, 4), dtype=f64, device=dev)
         stats = {}
         if k:
-            b = QPBatch(k, n, m, local_dev)
+            b = bobj
             try:
                 # shards are already in device memory: straight into the batch, no host bounce
                 b.load_ptr(shard[0].data_ptr(), shard[1].data_ptr(), shard[2].data_ptr(), shard[3].data_ptr(),

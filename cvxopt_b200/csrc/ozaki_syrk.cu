@@ -333,6 +333,286 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two-SM variant (tcgen05 cta_group::2): a cluster of two CTAs (the two SMs of one TPC) computes the
+// 256 x 128 block { (I0, J), (I1 = I0 + 1, J) } with M = 256 MMAs issued by the leader (cluster rank 0).
+// Each CTA stages its own 128 rows of the M operand (nS units of 4 KB per k step) and HALF of the N
+// operand (rows 64*rank .. 64*rank+63 of every unit of column block J: nS pieces of 2 KB), so a pair moves
+// 12 KB * nS per k step where two one-SM tiles move 16 KB * nS: the kernel is bound by operand ingest
+// (profiles/r01k), this is the -25 % of DESIGN.md's round-2 plan.  Conventions follow the vendored CUTLASS
+// sm100 headers (cute/arch/tmem_allocator_sm100.hpp Allocator2Sm, mma_sm100_umma.hpp SM100_MMA_S8_2x1SM_SS,
+// cutlass/arch/barrier.h umma_arrive_multicast_2x1SM):
+//   * tcgen05.alloc / dealloc / relinquish .cta_group::2 by the same warp (1) of BOTH CTAs;
+//   * the leader alone issues tcgen05.mma.cta_group::2 (idesc M = 256); descriptors hold the leader's
+//     shared-memory offsets, the peer's operands sit at the same offsets of its own shared memory;
+//     D rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's, same columns;
+//   * stage-full: every CTA's bulk copies complete on its own mbarrier; the peer's warp 1 relays each
+//     completion with a remote mbarrier.arrive on the leader's `pfull` barrier (shared::cluster address with
+//     the CTA-rank bit cleared, cute's Sm100MmaPeerBitMask);
+//   * stage-empty / accumulator-full: tcgen05.commit.cta_group::2 ... multicast::cluster with mask 0b11 arrives
+//     on the barrier at the same offset in both CTAs; accumulator-empty: the 4 epilogue warps of both CTAs
+//     arrive on the leader's barrier (count 8).
+constexpr uint32_t OZ_PEER_MASK = 0xFEFFFFFFu;
+constexpr uint32_t OZ_IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((OZ_T / 8) << 17) | ((2 * OZ_T / 16) << 24);
+constexpr int OZ_HALF = OZ_UNIT / 2;       // 2 KB: 64 rows of a unit
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {     // addr: shared::cluster address
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITC_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONEC_%=;\n\t"
+        "bra WAITC_%=;\n\t"
+        "DONEC_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit2_mc(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma2_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// one k step of a pass (levels D0..D1): A slices are 4 KB units, B slices 2 KB half units
+template <int D0, int D1, bool FIRST>
+__device__ __forceinline__ void oz_issue_step2(uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t tmem_base) {
+    constexpr int NS = D1 + 1;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s * (OZ_UNIT >> 4));
+#pragma unroll
+        for (int tt = 0; tt < NS; ++tt) {
+            if (s + tt >= D0 && s + tt <= D1) {
+                const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(b_lo + tt * (OZ_HALF >> 4));
+                tc_mma2_i8(tmem_base + (s + tt - D0) * OZ_T, da, db, OZ_IDESC2, (FIRST && s == 0) ? 0u : 1u);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
+    extern __shared__ uint8_t oz_smem_raw[];
+    __shared__ uint32_t tmem_base_sh;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OZ_RING * OZ_UNIT);
+    uint64_t *full = bars, *empty = bars + OZ_MAXST, *pfull = bars + 2 * OZ_MAXST, *acc_full = bars + 3 * OZ_MAXST,
+             *acc_empty = bars + 3 * OZ_MAXST + 1;
+
+    // pair (a, J): row blocks 2a (leader) and 2a + 1 (peer), column block J
+    const unsigned int tl = p.tiles[blockIdx.x >> 1];
+    const int a = (int)(tl >> 16), J = (int)(tl & 0xFFFFu);
+    int I = 2 * a + (int)rank;
+    const bool live = I < p.nblk;                // odd nblk: the last pair has no second row block
+    if (!live) I = 2 * a;                        // load valid data, store nothing
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ_MAXST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(pfull + s, 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();                          // both CTAs' barriers exist before anyone signals them
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    dbg_put(p, 0, 0x100u + (tid == 0));
+
+    const int S = p.S;
+    const int npass = p.npass;
+    const int nrange = (p.nk + OZ_KRANGE - 1) / OZ_KRANGE;
+    // stage of a pass: nS units of A (4 KB) then nS half units of B (2 KB)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t filled = 0, epar = 0;
+            for (int rg = 0; rg < nrange; ++rg) {
+                const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
+                for (int ps = 0; ps < npass; ++ps) {
+                    const int nS = min(S, p.pd1[ps] + 1);
+                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + OZ_HALF);
+                    const int nst = min(OZ_MAXST, (OZ_RING * OZ_UNIT) / (int)sbytes);
+                    for (int s2 = 0; s2 < OZ_MAXST; ++s2)
+                        if ((filled >> s2) & 1u) mbar_wait(empty + s2, (epar >> s2) & 1u);
+                    int st = 0;
+                    for (int kc = k0; kc < k1; ++kc) {
+                        if ((filled >> st) & 1u) { mbar_wait(empty + st, (epar >> st) & 1u); epar ^= 1u << st; }
+                        else filled |= 1u << st;
+                        mbar_expect_tx(full + st, sbytes);
+                        uint8_t *sa = smem + (size_t)st * sbytes;
+                        bulk_g2s(sa, p.Q + ((size_t)I * p.nk + kc) * (size_t)S * OZ_UNIT, (uint32_t)nS * OZ_UNIT, full + st);
+                        const uint8_t *qb = p.Q + ((size_t)J * p.nk + kc) * (size_t)S * OZ_UNIT + (size_t)rank * OZ_HALF;
+                        uint8_t *sb = sa + (size_t)nS * OZ_UNIT;
+                        for (int s = 0; s < nS; ++s) bulk_g2s(sb + (size_t)s * OZ_HALF, qb + (size_t)s * OZ_UNIT, OZ_HALF, full + st);
+                        if (++st == nst) st = 0;
+                    }
+                }
+            }
+            dbg_put(p, 1, 0x200u + rank);
+        }
+    } else if (warp == 1) {
+        uint32_t cpar = 0;
+        int g = 0;
+        if (!leader) {
+            // ===== peer: relay "my stage is full" to the leader =====
+            const uint32_t pf0 = smem_u32(pfull) & OZ_PEER_MASK;
+            for (int rg = 0; rg < nrange; ++rg) {
+                const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
+                for (int ps = 0; ps < npass; ++ps) {
+                    const int nS = min(S, p.pd1[ps] + 1);
+                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + OZ_HALF);
+                    const int nst = min(OZ_MAXST, (OZ_RING * OZ_UNIT) / (int)sbytes);
+                    int st = 0;
+                    for (int kc = k0; kc < k1; ++kc) {
+                        mbar_wait(full + st, (cpar >> st) & 1u);
+                        cpar ^= 1u << st;
+                        if (lane == 0) mbar_arrive_cluster(pf0 + (uint32_t)st * 8u);
+                        __syncwarp();
+                        if (++st == nst) st = 0;
+                    }
+                }
+            }
+        } else {
+            // ===== leader: MMA issue for both SMs =====
+            const uint32_t hi = (256u >> 4) | (1u << 14) | (6u << 29);      // SW32, K-major, 8-row groups 256 B apart
+            const uint32_t sbase = smem_u32(smem);
+            for (int rg = 0; rg < nrange; ++rg) {
+                const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
+                for (int ps = 0; ps < npass; ++ps, ++g) {
+                    const int d0 = p.pd0[ps], d1 = p.pd1[ps];
+                    const int nS = min(S, d1 + 1);
+                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + OZ_HALF);
+                    const int nst = min(OZ_MAXST, (OZ_RING * OZ_UNIT) / (int)sbytes);
+                    const int code = (nS == d1 + 1) ? d0 * 16 + d1 : -1;
+                    if (g > 0) { mbar_wait_cluster(acc_empty, (uint32_t)(g - 1) & 1); tc_fence_after(); }
+                    uint32_t touched = 0;
+                    int st = 0;
+                    for (int kc = k0; kc < k1; ++kc) {
+                        mbar_wait(full + st, (cpar >> st) & 1u);
+                        mbar_wait_cluster(pfull + st, (cpar >> st) & 1u);
+                        cpar ^= 1u << st;
+                        tc_fence_after();
+                        const uint32_t a0 = sbase + (uint32_t)st * sbytes;
+                        const uint32_t b0 = a0 + (uint32_t)nS * OZ_UNIT;
+                        const bool firstk = (kc == k0);
+                        if (elect_one()) {
+#define OZ_CASE2(D0, D1)                                                                             \
+    case (D0) * 16 + (D1):                                                                           \
+        if (firstk) oz_issue_step2<D0, D1, true>(a0 >> 4, b0 >> 4, hi, tmem_base);                   \
+        else oz_issue_step2<D0, D1, false>(a0 >> 4, b0 >> 4, hi, tmem_base);                         \
+        break;
+                            switch (code) {
+                                OZ_CASE2(0, 0) OZ_CASE2(1, 4) OZ_CASE2(5, 8)
+                                OZ_CASE2(0, 1) OZ_CASE2(2, 4)
+                                OZ_CASE2(0, 3) OZ_CASE2(4, 7)
+                                OZ_CASE2(2, 5) OZ_CASE2(6, 8) OZ_CASE2(8, 8)
+                            default:
+                                for (int s = 0; s < nS; ++s) {
+                                    const int tlo = max(0, d0 - s), thi = min(nS - 1, d1 - s);
+                                    const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(((a0 + s * OZ_UNIT) >> 4) & 0x3FFFu);
+                                    for (int tt = tlo; tt <= thi; ++tt) {
+                                        const int lev = s + tt - d0;
+                                        const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(((b0 + tt * OZ_HALF) >> 4) & 0x3FFFu);
+                                        tc_mma2_i8(tmem_base + lev * OZ_T, da, db, OZ_IDESC2, (touched >> lev) & 1u);
+                                        touched |= 1u << lev;
+                                    }
+                                }
+                            }
+#undef OZ_CASE2
+                            tc_commit2_mc(empty + st);       // frees the stage in BOTH CTAs once these MMAs have read it
+                        }
+                        __syncwarp();
+                        if (++st == nst) st = 0;
+                    }
+                    if (elect_one()) { tc_commit2_mc(acc_full); dbg_put(p, 2, 0x300u + g); }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): warp w owns TMEM lanes 32*(w%4) .. +31 of ITS OWN SM =====
+        const int quad = warp & 3;
+        const int row = I * OZ_T + quad * 32 + lane;
+        const bool row_ok = live && row < p.n;
+        const double rsc = row_ok ? p.cs[row] : 0.0;
+        const uint32_t ae = smem_u32(acc_empty) & OZ_PEER_MASK;      // the leader's barrier
+        int g = 0;
+        for (int rg = 0; rg < nrange; ++rg) {
+            for (int ps = 0; ps < npass; ++ps, ++g) {
+                const int d0 = p.pd0[ps], nlev = p.pd1[ps] - d0 + 1;
+                mbar_wait(acc_full, (uint32_t)g & 1);
+                tc_fence_after();
+                const double lsc = ldexp(1.0, -12 - 7 * (d0 + nlev - 1));
+                const bool first = (g == 0);
+                for (int c0 = 0; c0 < OZ_T; c0 += 16) {
+                    uint32_t r[4][16];
+                    const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
+                    tc_ld16(ta, r[0]);
+                    if (nlev > 1) tc_ld16(ta + OZ_T, r[1]);
+                    if (nlev > 2) tc_ld16(ta + 2 * OZ_T, r[2]);
+                    if (nlev > 3) tc_ld16(ta + 3 * OZ_T, r[3]);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int col = J * OZ_T + c0 + c;
+                        double v = (double)(int)r[0][c];
+                        if (nlev > 1) v = fma(v, 128.0, (double)(int)r[1][c]);
+                        if (nlev > 2) v = fma(v, 128.0, (double)(int)r[2][c]);
+                        if (nlev > 3) v = fma(v, 128.0, (double)(int)r[3][c]);
+                        if (row_ok && col < p.n && col <= row) {
+                            v = (v * lsc) * rsc * p.cs[col];
+                            double *dst = p.C + row + (size_t)col * p.ldc;
+                            if (first) v += (p.D ? p.beta * p.D[row + (size_t)col * p.ldd] : 0.0);
+                            else v += *dst;
+                            *dst = v;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ae);
+                if (quad == 0 && lane == 0) dbg_put(p, 3, 0x400u + g);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // the peer's shared memory / TMEM stay alive until the leader's MMAs are done
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // amax[j] = max_k |d[k] * A[k,j]|  ->  cs[j] = 2^e_j, sinv[j] = 64 * 2^-e_j
 __global__ void oz_colscale_kernel(int m, int n, const double *A, long long lda, const double *d, double *cs, double *sinv) {
     __shared__ double sh[32];
@@ -455,6 +735,7 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     static DeviceOnce once;
     if (const unsigned long long bit = once.pending()) {
         CVXB_CUDA(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        CVXB_CUDA(cudaFuncSetAttribute(oz_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
         once.mark(bit);
     }
     const int nblk = (n + OZ_T - 1) / OZ_T, nk = std::max(1, (m + OZ_KS - 1) / OZ_KS);
@@ -468,16 +749,33 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     // flight form a compact block (few distinct operand streams -> L2 hits instead of HBM reads)
     // (rebuilt per call: a few microseconds, and no shared mutable state between threads / handles; the
     // pageable-source copy is staged before cudaMemcpyAsync returns)
+    // CVXB_OZ_2SM=0 keeps the one-SM kernel (default: two-SM pairs, layout 0 only)
+    bool two_sm = layout == 0;
+    if (const char *e = getenv("CVXB_OZ_2SM")) two_sm = two_sm && e[0] != '0';
     std::vector<unsigned int> order;
     order.reserve((size_t)tiles);
     int band = 12;
     if (const char *e = getenv("CVXB_OZ_BAND")) band = std::max(1, atoi(e));
-    for (int r0 = 0; r0 < nblk; r0 += band) {
-        const int r1 = std::min(nblk, r0 + band);
-        for (int J = 0; J < r1; ++J)
-            for (int I = std::max(r0, J); I < r1; ++I) order.push_back(((unsigned)I << 16) | (unsigned)J);
+    long long npairs = 0;
+    if (two_sm) {
+        // pairs of row blocks (2a, 2a+1) x column block J with 2a+1 >= J (the tile (2a, J) of a pair that
+        // straddles the diagonal is computed and masked), same band-major launch order
+        const int na = (nblk + 1) / 2, pband = std::max(1, band / 2);
+        for (int a0 = 0; a0 < na; a0 += pband) {
+            const int a1 = std::min(na, a0 + pband);
+            for (int J = 0; J < nblk && J <= 2 * a1 - 1; ++J)
+                for (int a = std::max(a0, J / 2); a < a1; ++a)
+                    if (2 * a + 1 >= J) order.push_back(((unsigned)a << 16) | (unsigned)J);
+        }
+        npairs = (long long)order.size();
+    } else {
+        for (int r0 = 0; r0 < nblk; r0 += band) {
+            const int r1 = std::min(nblk, r0 + band);
+            for (int J = 0; J < r1; ++J)
+                for (int I = std::max(r0, J); I < r1; ++I) order.push_back(((unsigned)I << 16) | (unsigned)J);
+        }
     }
-    CVXB_CUDA(cudaMemcpyAsync(dtiles, order.data(), (size_t)tiles * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+    CVXB_CUDA(cudaMemcpyAsync(dtiles, order.data(), order.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
     oz_colscale_kernel<<<n, 256, 0, st>>>(m, n, A, lda, d, cs, sinv);
     count_launch();
     oz_slice_kernel<<<dim3(nk, nblk), OZ_T, 0, st>>>(m, n, A, lda, d, sinv, Q, nk, S, layout);
@@ -486,7 +784,20 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     p.Q = Q; p.cs = cs; p.D = D; p.ldd = ldd; p.C = C; p.ldc = ldc; p.beta = beta;
     p.n = n; p.nblk = nblk; p.nk = nk; p.S = S; p.layout = layout; p.dbg = dbg; p.tiles = dtiles;
     oz_choose_groups(S, &p.npass, p.pd0, p.pd1);
-    oz_mma_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM, st>>>(p);
+    if (two_sm) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * npairs), 1, 1);
+        cfg.blockDim = dim3(OZ_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = OZ_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CVXB_CUDA(cudaLaunchKernelEx(&cfg, oz_mma2_kernel, p));
+    } else {
+        oz_mma_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM, st>>>(p);
+    }
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;

@@ -37,7 +37,7 @@ def relerr(a, b):
 
 def cond1(L, K1norm):
     """1-norm condition number of K = L L' from its Cholesky factor (LAPACK dpocon)."""
-    rcond, info = sla.lapack.dpocon(L, K1norm, lower=1)
+    rcond, info = sla.lapack.dpocon(L, K1norm, uplo='L')
     assert info == 0
     return 1.0 / max(rcond, 1e-300)
 
