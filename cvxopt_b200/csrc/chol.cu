@@ -591,8 +591,10 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             if (w.panel[i]) CVXB_CUDA(cudaFree(w.panel[i]));
             w.panel[i] = nullptr;
         }
+        // two group buffers, each holding the TRSM results of a PAIR of consecutive panels side by side
+        // (rows x 2 NB), so that the bulk trailing update of a pair is one K = 256 product
         const int rows = (n + 1) & ~1;
-        for (int i = 0; i < 2; ++i) CVXB_CUDA(cudaMalloc(&w.panel[i], (size_t)rows * NB * sizeof(double)));
+        for (int i = 0; i < 2; ++i) CVXB_CUDA(cudaMalloc(&w.panel[i], (size_t)rows * 2 * NB * sizeof(double)));
         w.panel_rows = rows;
     }
     while ((int)w.ev_dg.size() < nblk) {
@@ -612,6 +614,22 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
     CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_start, 0));
     CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_start, 0));
     CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_start, 0));
+    // Pair aggregation of the bulk update (CVXB_CHOL_PAIR=0 restores one bulk update per panel):
+    //   even step 2g  : TRSM -> group buffer columns [0, NB);  C0 (K = NB) completes block column 2g+1;
+    //                   D0: diagonal tile (2g+2, 2g+2) -= its panel-2g part (the only tile of block column 2g+2
+    //                   the diagonal chain needs before the pair's bulk update exists); NO bulk update.
+    //   odd step 2g+1 : TRSM -> columns [NB, 2 NB);  C0 with K = 2 NB (panels 2g and 2g+1) completes block
+    //                   column 2g+2 below its diagonal tile;  bulk R with K = 2 NB on block columns >= 2g+3.
+    // A K = 128 update keeps the DMMA pipe 63 % busy (prologue + read-modify-write epilogue per 8 k steps,
+    // profiles/r01e); K = 256 halves the C traffic and the per-tile overhead of the bulk flops.
+    static int pair_mode = -1;
+    if (pair_mode < 0) {
+        const char *e = getenv("CVXB_CHOL_PAIR");
+        pair_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool pair = pair_mode == 1;
+    int last_r = -1;                       // last step that recorded ev_r
+    int prev_r = -1;                       // the one before
     for (int jb = 0; jb < nblk; ++jb) {
         const int j = jb * NB;
         const int wj = (n - j < NB) ? (n - j) : NB;
@@ -619,10 +637,22 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         double *Ajj = A + j + (long long)j * lda;
         double *invj = inv + (long long)jb * NB * NB;
         double *invTj = inv + (long long)(nblk + jb) * NB * NB;
-        // ---- D: diagonal block ----
+        const bool odd = pair && (jb & 1);
+        // Group buffer of this step.  Its row r is global row R0 + r, R0 = first row below the EVEN panel's
+        // diagonal block, for both panels of the pair: the odd panel's TRSM result therefore sits at column
+        // offset NB and row offset NB.  `Wo` = buffer row of this step's first trailing row (A22).
+        double *Wg = pair ? w.panel[(jb >> 1) & 1] : w.panel[jb & 1];
+        double *Wp = Wg + (odd ? (long long)NB * ldw + NB : 0);
+        double *Wo = Wg + (odd ? NB : 0);
+        // ---- D: diagonal block.  Needs A(jb,jb) updated through panel jb-2 and the raw tile A(jb,jb-1)
+        // (block column jb-1 complete through panel jb-2): C0(jb-2) [which follows D0(jb-2) on T] and the
+        // last bulk update that touched block column jb.
         if (jb >= 2) {
             CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_c0[jb - 2], 0));
-            if (w.r_valid[(jb - 2) & 1] == jb - 2) CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_r[jb - 2], 0));
+            // the latest bulk update issued at a step <= jb-2 (a later one belongs to panels the prologue
+            // applies itself, waiting for it would serialise the chain behind the bulk work)
+            const int rd = (last_r <= jb - 2) ? last_r : prev_r;
+            if (rd >= 0) CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_r[rd], 0));
         }
         const double *Tprev = jb > 0 ? A + j + (long long)(j - NB) * lda : nullptr;
         const double *invprev = jb > 0 ? inv + (long long)(jb - 1) * NB * NB : nullptr;
@@ -632,13 +662,14 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         CVXB_LAUNCH_CHECK();
         CVXB_CUDA(cudaEventRecord(w.ev_dg[jb], D));
         // L(j:, j-1) goes back into A once Dg(jb) has consumed the raw tile; the copy rides on the
-        // panel stream T behind this step's TRSM / column update (it used to sit on D, where its
-        // 3-5 us were part of the diagonal chain)
+        // panel stream T behind this step's TRSM / column update
         auto copy_back_prev = [&]() -> int {
             if (jb == 0) return 0;
             const int jp = j - NB, mp = n - j;
+            const int pb = jb - 1;
+            const double *src = pair ? w.panel[(pb >> 1) & 1] + ((pb & 1) ? (long long)NB * ldw + NB : 0) : w.panel[pb & 1];
             CVXB_CUDA(cudaMemcpy2DAsync(A + j + (long long)jp * lda, (size_t)lda * sizeof(double),
-                                        w.panel[(jb - 1) & 1], (size_t)ldw * sizeof(double),
+                                        src, (size_t)ldw * sizeof(double),
                                         (size_t)mp * sizeof(double), NB, cudaMemcpyDeviceToDevice, T));
             return 0;
         };
@@ -649,9 +680,10 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         }
         double *A21 = Ajj + wj;
         double *A22 = A21 + (long long)wj * lda;
-        double *Wp = w.panel[jb & 1];
         // ---- T: panel TRSM as a GEMM with the block inverse (out of place) ----
         CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_dg[jb], 0));
+        // the group buffer about to be overwritten was read by the bulk update two groups (steps) ago
+        if (!odd && prev_r >= 0) CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_r[prev_r], 0));
         {
             GemmDesc g;
             g.M = m; g.N = wj; g.K = wj;
@@ -662,14 +694,34 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             CVXB_TRY(dmma_gemm(g, T));
         }
         CVXB_CUDA(cudaEventRecord(w.ev_tr[jb], T));
-        // ---- T: next block column, rows below its diagonal block ----
+        // every later write of this step into block columns >= jb+1 is ordered behind the last bulk update
+        if (last_r >= 0) CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_r[last_r], 0));
         const int wn = (m < NB) ? m : NB;          // width of block column jb+1
+        // ---- T (even step of a pair): diagonal tile of block column jb+2 gets its panel-jb part now ----
+        if (pair && !odd && m > NB) {
+            const int w2 = (m - NB < NB) ? (m - NB) : NB;
+            GemmDesc d0;
+            d0.M = w2; d0.N = w2; d0.K = wj;
+            d0.X = Wp + NB; d0.ldx = ldw; d0.x_kmajor = false;
+            d0.Y = Wp + NB; d0.ldy = ldw; d0.y_kmajor = false;
+            double *tile = A22 + NB + (long long)NB * lda;
+            d0.D = tile; d0.ldd = lda; d0.C = tile; d0.ldc = lda;
+            d0.alpha = -1.0; d0.beta = 1.0; d0.lower_only = true;
+            CVXB_TRY(dmma_gemm(d0, T));
+        }
+        // ---- T: next block column, rows below its diagonal block ----
         if (m > wn) {
-            if (jb >= 1 && w.r_valid[(jb - 1) & 1] == jb - 1) CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_r[jb - 1], 0));
             GemmDesc c;
-            c.M = m - wn; c.N = wn; c.K = wj;
-            c.X = Wp + wn; c.ldx = ldw; c.x_kmajor = false;
-            c.Y = Wp; c.ldy = ldw; c.y_kmajor = false;
+            c.M = m - wn; c.N = wn;
+            if (odd) {          // both panels of the pair: rows of the group buffer, K = NB + wj
+                c.K = NB + wj;
+                c.X = Wo + wn; c.Y = Wo;
+            } else {
+                c.K = wj;
+                c.X = Wp + wn; c.Y = Wp;
+            }
+            c.ldx = ldw; c.x_kmajor = false;
+            c.ldy = ldw; c.y_kmajor = false;
             c.D = A22 + wn; c.ldd = lda; c.C = A22 + wn; c.ldc = lda;
             c.alpha = -1.0; c.beta = 1.0;
             c.trace = w.trace ? w.trace + 8 * jb + 4 : nullptr;
@@ -678,19 +730,22 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         CVXB_CUDA(cudaEventRecord(w.ev_c0[jb], T));
         CVXB_TRY(copy_back_prev());
         // ---- U: the rest of the trailing matrix ----
-        if (m > NB) {
+        if (m > NB && (!pair || odd)) {
             CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_tr[jb], 0));
             GemmDesc u;
-            u.M = m; u.N = m; u.K = wj;
-            u.X = Wp; u.ldx = ldw; u.x_kmajor = false;
-            u.Y = Wp; u.ldy = ldw; u.y_kmajor = false;
+            u.M = m; u.N = m;
+            if (odd) { u.K = NB + wj; u.X = Wo; u.Y = Wo; }
+            else { u.K = wj; u.X = Wp; u.Y = Wp; }
+            u.ldx = ldw; u.x_kmajor = false;
+            u.ldy = ldw; u.y_kmajor = false;
             u.D = A22; u.ldd = lda; u.C = A22; u.ldc = lda;
             u.alpha = -1.0; u.beta = 1.0; u.lower_only = true;
             u.ct_begin = panel_tiles; u.ct_end = 1 << 30;
             u.trace = w.trace ? w.trace + 8 * jb + 6 : nullptr;
             CVXB_TRY(dmma_gemm(u, U));
             CVXB_CUDA(cudaEventRecord(w.ev_r[jb], U));
-            w.r_valid[jb & 1] = jb;
+            prev_r = last_r;
+            last_r = jb;
         }
     }
     w.r_valid[0] = w.r_valid[1] = -1;

@@ -138,18 +138,32 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((OZ_T / 8) <
 // One k step of a pass whose level range is known at compile time: a straight-line MMA sequence
 // (the tensor pipe retires a 128x128x32 int8 MMA every 64 cycles; a runtime pair loop issues too slowly).
 // The first k step of a pass overwrites each accumulator with its first product (s == 0), later ones add.
+// N = 256 instruction descriptor: one MMA multiplies A slice s with TWO consecutive B slices (t, t+1), which
+// sit back to back in shared memory and whose products belong to the adjacent levels s+t, s+t+1 = adjacent
+// 128-column accumulators.  The tensor pipe reads its operands from shared memory: a 128x128x32 int8 MMA
+// reads 8 KB per 64 cycles = the full 128 B/cycle of the SM, so the bulk copies that refill the ring compete
+// with it (the one-slice-pair kernel was 64 % busy, profiles/r01k); a 128x256x32 MMA reads 12 KB per 128 cycles.
+constexpr uint32_t OZ_IDESC_N256 = (2u << 4) | (1u << 7) | (1u << 10) | ((2 * OZ_T / 8) << 17) | ((OZ_T / 16) << 24);
+
 template <int D0, int D1, bool FIRST>
 __device__ __forceinline__ void oz_issue_step(uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t tmem_base) {
     constexpr int NS = D1 + 1;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s * (OZ_UNIT >> 4));
+        // B slices t with D0 <= s + t <= D1, 0 <= t < NS: a compile-time range, walked two at a time
+        const int tlo = (D0 - s) > 0 ? (D0 - s) : 0;
+        const int thi = (D1 - s) < (NS - 1) ? (D1 - s) : (NS - 1);
 #pragma unroll
-        for (int tt = 0; tt < NS; ++tt) {
-            if (s + tt >= D0 && s + tt <= D1) {
-                const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(b_lo + tt * (OZ_UNIT >> 4));
-                tc_mma_i8(tmem_base + (s + tt - D0) * OZ_T, da, db, OZ_IDESC, (FIRST && s == 0) ? 0u : 1u);
-            }
+        for (int tt = 0; tt < NS; tt += 1) {
+            if (tt < tlo || tt > thi) continue;
+            if (((tt - tlo) & 1) != 0) continue;                 // second half of a pair: already issued
+            const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(b_lo + tt * (OZ_UNIT >> 4));
+            const uint32_t acc = (FIRST && s == 0) ? 0u : 1u;
+            if (tt + 1 <= thi)
+                tc_mma_i8(tmem_base + (s + tt - D0) * OZ_T, da, db, OZ_IDESC_N256, acc);
+            else
+                tc_mma_i8(tmem_base + (s + tt - D0) * OZ_T, da, db, OZ_IDESC, acc);
         }
     }
 }
@@ -749,9 +763,11 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     // flight form a compact block (few distinct operand streams -> L2 hits instead of HBM reads)
     // (rebuilt per call: a few microseconds, and no shared mutable state between threads / handles; the
     // pageable-source copy is staged before cudaMemcpyAsync returns)
-    // CVXB_OZ_2SM=0 keeps the one-SM kernel (default: two-SM pairs, layout 0 only)
-    bool two_sm = layout == 0;
-    if (const char *e = getenv("CVXB_OZ_2SM")) two_sm = two_sm && e[0] != '0';
+    // CVXB_OZ_2SM=1 selects the two-SM (cta_group::2) kernel.  Measured on B200 (profiles/r02c): correct, but a
+    // 256x128x32 int8 MMA issued for the SM pair takes 128 cycles (the pair runs at the rate of ONE SM's
+    // 128x128x32), so 21.5-24.8 ms against 18.5 ms for the one-SM kernel at n=8192, m=16384: off by default.
+    bool two_sm = false;
+    if (const char *e = getenv("CVXB_OZ_2SM")) two_sm = layout == 0 && e[0] == '1';
     std::vector<unsigned int> order;
     order.reserve((size_t)tiles);
     int band = 12;
