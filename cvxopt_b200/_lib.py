@@ -41,6 +41,7 @@ _SIGS = {
     "cvxb_kkt_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(Dims),
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "cvxb_kkt_destroy": (None, [C.c_void_p]),
+    "cvxb_kkt_set_method": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "cvxb_kkt_set_H": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "cvxb_kkt_factor": (C.c_int, [C.c_void_p, C.POINTER(Scaling), C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -71,6 +72,10 @@ _SIGS = {
     "cvxb_triusc": (C.c_int, [C.c_void_p, C.POINTER(Dims), C.c_int]),
     "cvxb_sdot": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Dims), c_double_p, C.c_int]),
     "cvxb_max_step": (C.c_int, [C.c_void_p, C.POINTER(Dims), c_double_p, c_double_p, C.c_int]),
+    "cvxb_compute_scaling": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Dims), C.POINTER(Scaling),
+                                       C.c_int]),
+    "cvxb_update_scaling": (C.c_int, [C.POINTER(Scaling), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Dims),
+                                      C.c_int]),
     "cvxb_syrk_scaled": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "cvxb_syrk_scaled_i8": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

@@ -614,7 +614,9 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
     CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_start, 0));
     CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_start, 0));
     CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_start, 0));
-    // Pair aggregation of the bulk update (CVXB_CHOL_PAIR=0 restores one bulk update per panel):
+    // Pair aggregation of the bulk update (opt-in, CVXB_CHOL_PAIR=1; measured slower on B200 — potrf 10.99 ms
+    // against 10.31 ms at n=8192, 3.13 against 2.92 ms at n=4096, profiles/r02e — because the K = 256 column
+    // update of the odd steps lengthens the panel path while the chain, not the bulk rate, sets the pace):
     //   even step 2g  : TRSM -> group buffer columns [0, NB);  C0 (K = NB) completes block column 2g+1;
     //                   D0: diagonal tile (2g+2, 2g+2) -= its panel-2g part (the only tile of block column 2g+2
     //                   the diagonal chain needs before the pair's bulk update exists); NO bulk update.
@@ -625,7 +627,7 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
     static int pair_mode = -1;
     if (pair_mode < 0) {
         const char *e = getenv("CVXB_CHOL_PAIR");
-        pair_mode = (e && e[0] == '0') ? 0 : 1;
+        pair_mode = (e && e[0] == '1') ? 1 : 0;
     }
     const bool pair = pair_mode == 1;
     int last_r = -1;                       // last step that recorded ev_r

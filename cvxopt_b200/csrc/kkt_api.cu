@@ -52,52 +52,9 @@ static int check_device(int device) {
 
 using namespace cvxb;
 
-struct cvxb_kkt {
-    int device = 0;
-    int n = 0, p = 0;
-    ConeLayout cone;
-    const double *G = nullptr;   // cdim x n, rows [mnl, cdim) hold G (rows [0,mnl) belong to Df)
-    long long ldg = 0;
-    bool own_G = false;
-    double *Hres = nullptr;      // resident H (symmetrised), or null
-    double *Hbuf = nullptr;      // per-call H upload buffer (lazy)
-    double *Kmat = nullptr;      // n x n: normal equations, then its Cholesky factor (lower)
-    double *inv = nullptr;       // inverses of the diagonal blocks of L
-    double *Gs = nullptr;        // scaled+packed rows that are not 'l': [mnl | q | s packed] x n
-    long long ldgs = 0;
-    int nrest = 0;
-    double *Gunp = nullptr;      // unpacked scaled 's' rows (sums2 x n) — only when ns > 0
-    double *Dfbuf = nullptr;     // mnl x n upload buffer
-    // equality constraints (p > 0), kkt_chol2-style elimination (reference misc.py:1464-1472):
-    double *Aeq = nullptr;       // p x n (ld lda_eq)
-    long long lda_eq = 0;
-    double *Asct = nullptr;      // n x p: L^{-1} A'
-    long long ldas = 0;
-    double *Kp = nullptr;        // p x p: Asct' Asct, then its Cholesky factor
-    long long ldkp = 0;
-    double *invp = nullptr;      // diagonal-block inverses of chol(Kp)
-    double *yd = nullptr;        // p
-    bool singular = false;       // first factorisation failed -> S += A'A from then on (misc.py:1433-1447)
-    bool first_factor = true;
-    DevScaling W;
-    double *bzp = nullptr, *zin = nullptr, *zt = nullptr, *xv = nullptr, *yv = nullptr;
-    double *gemv_ws = nullptr;
-    double *swork = nullptr;
-    size_t swork_doubles = 0;
-    CholWork cw;
-    cudaStream_t st = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, t0 = nullptr, t1 = nullptr;
-    double factor_ms = 0, solve_ms = 0, br[3] = {0, 0, 0};
-    bool factored = false;
-    // SYRK of the 'l' rows on the int8 tensor path (ozaki_syrk.cu): 0 off (DMMA kernel), 1 for large
-    // problems (where it measured faster), 2 always.  CVXB_OZAKI=0/1/2 read at create; unset = 1.
-    int i8_mode = 1;
-    void *oz_work = nullptr;
-    size_t oz_bytes = 0;
-    int syrk_path = 0;           // kernel of the last factor's 'l'-row SYRK: 0 none, 1 fp64 DMMA, 2 int8 slices
-};
+#include "kkt_internal.cuh"
 
-namespace {
+namespace cvxb {
 
 int upload_matrix(double *dst, long long ldd, const double *src, long long lds, int rows, int cols,
                   int space, cudaStream_t st) {
@@ -116,7 +73,66 @@ int xfer_vec(double *dst, const double *src, size_t n, int space, bool to_device
     return 0;
 }
 
-}  // namespace
+// bzp := pack(W^{-T} bz)                                       (misc.py:1306-1307, :1626-1627)
+int kkt_pack_bz(cvxb_kkt *k, const double *zd) {
+    const ConeLayout &c = k->cone;
+    cudaStream_t st = k->st;
+    const int nlq = c.mnl + c.ml + c.sumq;
+    if (c.mnl > 0) CVXB_TRY(scale_rows(zd, c.cdim, k->bzp, c.cdim, c.mnl, 1, k->W.dnli, st));
+    if (c.ml > 0)
+        CVXB_TRY(scale_rows(zd + c.mnl, c.cdim, k->bzp + c.mnl, c.cdim, c.ml, 1, k->W.di, st));
+    if (c.nq > 0)
+        CVXB_TRY(scale_q(c, k->W, zd + c.mnl + c.ml, c.cdim, k->bzp + c.mnl + c.ml, c.cdim, 1, true, st));
+    if (c.ns > 0) {
+        CVXB_TRY(scale_s(c, k->W, zd + nlq, c.cdim, k->zt + nlq, c.cdim, 1, 'T', 'I', k->swork,
+                         k->swork_doubles, st));
+        CVXB_TRY(pack_s(c, k->zt + nlq, c.cdim, k->bzp + nlq, c.cdim, 1, true, st));
+    }
+    return 0;
+}
+
+// z := unpack(bzp)                                             (misc.py:1345, :1697)
+int kkt_unpack_z(cvxb_kkt *k, double *zd) {
+    const ConeLayout &c = k->cone;
+    cudaStream_t st = k->st;
+    const int nlq = c.mnl + c.ml + c.sumq;
+    if (nlq > 0)
+        CVXB_CUDA(cudaMemcpyAsync(zd, k->bzp, (size_t)nlq * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (c.ns > 0) CVXB_TRY(unpack_s(c, k->bzp + nlq, c.cdim, zd + nlq, c.cdim, 1, st));
+    return 0;
+}
+
+int trsm_lower_left(int n, const double *L, long long ldl, const double *inv, double *B, long long ldb, int ncols,
+                    cudaStream_t st) {
+    if (n <= 0 || ncols <= 0) return 0;
+    const int nblk = (n + NB - 1) / NB;
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int j = jb * NB;
+        const int wj = (n - j < NB) ? (n - j) : NB;
+        const int mrem = n - j - wj;
+        double *Bj = B + j;
+        {   // X_j = inv_jj * B_j   (in place: one tile row, every tile owns its columns)
+            GemmDesc g;
+            g.M = wj; g.N = ncols; g.K = wj;
+            g.X = inv + (long long)jb * NB * NB; g.ldx = NB; g.x_kmajor = false;
+            g.Y = Bj; g.ldy = (int)ldb; g.y_kmajor = true;
+            g.C = Bj; g.ldc = (int)ldb;
+            CVXB_TRY(dmma_gemm(g, st));
+        }
+        if (mrem > 0) {   // B[j+1:, :] -= L[j+1:, j] X_j
+            GemmDesc g;
+            g.M = mrem; g.N = ncols; g.K = wj;
+            g.X = L + (j + wj) + (long long)j * ldl; g.ldx = (int)ldl; g.x_kmajor = false;
+            g.Y = Bj; g.ldy = (int)ldb; g.y_kmajor = true;
+            g.D = Bj + wj; g.ldd = (int)ldb; g.C = Bj + wj; g.ldc = (int)ldb;
+            g.alpha = -1.0; g.beta = 1.0;
+            CVXB_TRY(dmma_gemm(g, st));
+        }
+    }
+    return 0;
+}
+
+}  // namespace cvxb
 
 extern "C" {
 
@@ -252,6 +268,7 @@ void cvxb_kkt_destroy(cvxb_kkt *k) {
                       k->zin, k->zt, k->xv, k->yv, k->gemv_ws, k->swork};
     for (double *b : bufs) if (b) cudaFree(b);
     if (k->oz_work) cudaFree(k->oz_work);
+    if (k->ext && k->ext_destroy) k->ext_destroy(k->ext);
     k->W.destroy();
     k->cone.destroy();
     chol_work_destroy(k->cw);
@@ -261,7 +278,17 @@ void cvxb_kkt_destroy(cvxb_kkt *k) {
     delete k;
 }
 
-static long long kkt_ldk(const cvxb_kkt *k) { long long l = (k->n + 1) & ~1; return l > 2 ? l : 2; }
+
+int cvxb_kkt_set_method(cvxb_kkt *k, int method, double kktreg) {
+    if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
+    if (k->method != 0 || k->factored) { set_error("set_method: call once, right after create"); return CVXB_E_ARG; }
+    CVXB_CUDA(cudaSetDevice(k->device));
+    if (method == 0) return 0;
+    if (method == 1) { CVXB_TRY(kkt_qr_setup(k)); k->method = 1; return 0; }
+    if (method == 2) { CVXB_TRY(kkt_ldl_setup(k, kktreg)); k->method = 2; return 0; }
+    set_error("set_method: unknown method %d", method);
+    return CVXB_E_ARG;
+}
 
 int cvxb_kkt_set_H(cvxb_kkt *k, const double *H, int ldh, int space) {
     if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
@@ -287,6 +314,13 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
                     const double *Df, int lddf, int use_resident_H, int space) {
     if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
     CVXB_CUDA(cudaSetDevice(k->device));
+    if (k->method == 1) {
+        if (H || Df || k->cone.mnl) { set_error("kkt_qr: the QR route solves systems with a zero (1,1) block (no H, no Df)"); return CVXB_E_ARG; }
+        k->factored = false;
+        int r = kkt_qr_factor(k, Wp, space);
+        k->factored = (r == 0);
+        return r;
+    }
     const ConeLayout &c = k->cone;
     const int n = k->n;
     cudaStream_t st = k->st;
@@ -394,48 +428,33 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
             CVXB_TRY(upload_matrix(k->Kmat, ldk, Hptr, ldH, n, n, CVXB_DEVICE, st));
         }
         CVXB_CUDA(cudaEventRecord(k->e2, st));
+        if (k->method == 2 && k->p > 0) {
+            // kkt_ldl2: Kmat now holds S = H + GG' W^-1 W^-T GG (lower); the 2x2 system [S A'; A 0] is factored
+            // with Bunch-Kaufman pivoting (lapack.sytrf, misc.py:1172).  p == 0 is a plain Cholesky there too (:1173).
+            CVXB_TRY(kkt_ldl_factor(k));
+            CVXB_CUDA(cudaMemcpyAsync(&info, k->cw.d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CVXB_CUDA(cudaStreamSynchronize(st));
+            return 0;
+        }
         CVXB_TRY(potrf_lower(n, k->Kmat, (int)ldk, k->inv, k->cw, st));
         CVXB_CUDA(cudaMemcpyAsync(&info, k->cw.d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
         CVXB_CUDA(cudaStreamSynchronize(st));
         return 0;
     };
-    CVXB_TRY(assemble_and_factor(k->singular));
-    if (info > 0 && k->p > 0 && k->first_factor && !k->singular) {
+    CVXB_TRY(assemble_and_factor(k->method == 2 ? false : k->singular));
+    if (info > 0 && k->p > 0 && k->first_factor && !k->singular && k->method != 2) {
         // S is singular on the first call: switch to S + A'A for the rest of the solve
         k->singular = true;
         info = 0;
         CVXB_TRY(assemble_and_factor(true));
     }
     k->first_factor = false;
-    if (info == 0 && k->p > 0) {
+    if (info == 0 && k->p > 0 && k->method != 2) {
         // Asct := L^{-1} A'  (blocked forward substitution with the diagonal-block inverses),
         // Kp := Asct' Asct,  Kp = Lp Lp'                               (misc.py:1464-1472)
         const int p = k->p;
         CVXB_TRY(transpose_copy(k->Aeq, k->lda_eq, k->Asct, k->ldas, p, n, st));
-        const int nblk = (n + NB - 1) / NB;
-        for (int jb = 0; jb < nblk; ++jb) {
-            const int j = jb * NB;
-            const int wj = (n - j < NB) ? (n - j) : NB;
-            const int mrem = n - j - wj;
-            double *Bj = k->Asct + j;
-            {   // X_j = inv_jj * B_j   (in place: one tile owns its columns)
-                GemmDesc g;
-                g.M = wj; g.N = p; g.K = wj;
-                g.X = k->inv + (long long)jb * NB * NB; g.ldx = NB; g.x_kmajor = false;
-                g.Y = Bj; g.ldy = (int)k->ldas; g.y_kmajor = true;
-                g.C = Bj; g.ldc = (int)k->ldas;
-                CVXB_TRY(dmma_gemm(g, st));
-            }
-            if (mrem > 0) {   // B[j+1:, :] -= L[j+1:, j] X_j
-                GemmDesc g;
-                g.M = mrem; g.N = p; g.K = wj;
-                g.X = k->Kmat + (j + wj) + (long long)j * ldk; g.ldx = (int)ldk; g.x_kmajor = false;
-                g.Y = Bj; g.ldy = (int)k->ldas; g.y_kmajor = true;
-                g.D = Bj + wj; g.ldd = (int)k->ldas; g.C = Bj + wj; g.ldc = (int)k->ldas;
-                g.alpha = -1.0; g.beta = 1.0;
-                CVXB_TRY(dmma_gemm(g, st));
-            }
-        }
+        CVXB_TRY(trsm_lower_left(n, k->Kmat, ldk, k->inv, k->Asct, k->ldas, p, st));
         {
             GemmDesc g;
             g.M = p; g.N = p; g.K = n;
@@ -468,6 +487,7 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
     if (!k->factored) { set_error("solve called before a successful factor"); return CVXB_E_ARG; }
     CVXB_CUDA(cudaSetDevice(k->device));
+    if (k->method == 1) return kkt_qr_solve(k, x, y, z, space);
     const ConeLayout &c = k->cone;
     const int n = k->n;
     cudaStream_t st = k->st;
@@ -482,17 +502,7 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
         xd = k->xv; zd = k->zin;
         if (k->p > 0) { CVXB_TRY(xfer_vec(k->yd, y, k->p, CVXB_HOST, true, st)); ydv = k->yd; }
     }
-    // bzp := pack(W^{-T} bz)                                   (misc.py:1306-1307)
-    if (c.mnl > 0) CVXB_TRY(scale_rows(zd, c.cdim, k->bzp, c.cdim, c.mnl, 1, k->W.dnli, st));
-    if (c.ml > 0)
-        CVXB_TRY(scale_rows(zd + c.mnl, c.cdim, k->bzp + c.mnl, c.cdim, c.ml, 1, k->W.di, st));
-    if (c.nq > 0)
-        CVXB_TRY(scale_q(c, k->W, zd + c.mnl + c.ml, c.cdim, k->bzp + c.mnl + c.ml, c.cdim, 1, true, st));
-    if (c.ns > 0) {
-        CVXB_TRY(scale_s(c, k->W, zd + nlq, c.cdim, k->zt + nlq, c.cdim, 1, 'T', 'I', k->swork,
-                         k->swork_doubles, st));
-        CVXB_TRY(pack_s(c, k->zt + nlq, c.cdim, k->bzp + nlq, c.cdim, 1, true, st));
-    }
+    CVXB_TRY(kkt_pack_bz(k, zd));
     // x := x + Gs' bzp                                            (misc.py:1311)
     if (c.ml > 0)
         CVXB_TRY(gemv_t(c.ml, n, k->G + c.mnl, k->ldg, k->W.di, k->bzp + c.mnl, 1.0, 1.0, xd, st));
@@ -500,7 +510,10 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     if (k->nrest - c.mnl > 0)
         CVXB_TRY(gemv_t(k->nrest - c.mnl, n, k->Gs + c.mnl, k->ldgs, nullptr,
                         k->bzp + c.mnl + c.ml, 1.0, 1.0, xd, st));
-    if (k->p == 0) {
+    if (k->method == 2 && k->p > 0) {
+        // [x; y] := (L D L')^{-1} [x; y]                          (lapack.sytrs, misc.py:1196)
+        CVXB_TRY(kkt_ldl_solve(k, xd, ydv));
+    } else if (k->p == 0) {
         // x := K^{-1} x                                           (misc.py:1327)
         CVXB_TRY(potrs_lower(n, k->Kmat, (int)ldk, k->inv, xd, k->cw, st));
     } else {
@@ -523,11 +536,7 @@ int cvxb_kkt_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     if (k->nrest - c.mnl > 0)
         CVXB_TRY(gemv_n(k->nrest - c.mnl, n, k->Gs + c.mnl, k->ldgs, nullptr, xd, 1.0, -1.0,
                         k->bzp + c.mnl + c.ml, k->gemv_ws, st));
-    // z := unpack(bzp)                                            (misc.py:1345)
-    if (nlq > 0)
-        CVXB_CUDA(cudaMemcpyAsync(zd, k->bzp, (size_t)nlq * sizeof(double),
-                                  cudaMemcpyDeviceToDevice, st));
-    if (c.ns > 0) CVXB_TRY(unpack_s(c, k->bzp + nlq, c.cdim, zd + nlq, c.cdim, 1, st));
+    CVXB_TRY(kkt_unpack_z(k, zd));
     if (space != CVXB_DEVICE) {
         CVXB_TRY(xfer_vec(x, k->xv, n, CVXB_HOST, false, st));
         CVXB_TRY(xfer_vec(z, k->zin, c.cdim, CVXB_HOST, false, st));

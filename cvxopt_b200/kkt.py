@@ -114,7 +114,9 @@ def make_scaling(W, ml, q, s, mnl=0):
 class KKTChol:
     """One `kkt_chol` factory instance: G (and optionally H) resident in HBM."""
 
-    def __init__(self, G, dims, A=None, mnl=0, H=None, device=0):
+    METHODS = {"chol": 0, "qr": 1, "ldl2": 2}
+
+    def __init__(self, G, dims, A=None, mnl=0, H=None, device=0, method="chol", kktreg=0.0):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         Gm = _mat(G, "G")
@@ -143,6 +145,10 @@ class KKTChol:
             C.byref(self._h), self.n, p, C.byref(self._cd), Gm.ctypes.data, max(1, Gm.shape[0]),
             Am.ctypes.data if (Am is not None and p) else None, max(1, p), _lib.HOST, device)
         _lib.check(rc, "kkt_chol")
+        self.method = method
+        if method != "chol":
+            _lib.check(self._lib.cvxb_kkt_set_method(self._h, self.METHODS[method], float(kktreg)),
+                       "kkt_%s" % method)
         self._H_resident = None
         if H is not None:
             self.set_H(H)
@@ -341,8 +347,15 @@ def kkt_ldl2(G, dims, A=None, mnl=0, H=None, device=0):
         [ H + GG' W^-1 W^-T GG   A' ] [ux]   [bx + GG' W^-1 W^-T bz]
         [ A                      0  ] [uy] = [by]
 
-    The reference factors it with sytrf (potrf when p = 0, :1172-1173).  The matrix is
-    quasi-definite, so its block L D L' with D = diag(I, -I) needs no pivoting:
-    L = [L11 0; A L11^-T  Lk] with S = L11 L11', A S^-1 A' = Lk Lk' -- which is the pair of
-    Cholesky factorizations KKTChol computes.  Same solution, all cones."""
-    return KKTChol(G, dims, A, mnl, H, device)
+    factored as P K P' = L D L' with Bunch-Kaufman pivoting on the device (the algorithm of lapack.sytrf, which the
+    reference calls at :1172; csrc/kkt_ldl.cu) and solved with the sweeps of lapack.sytrs (:1196).  With no
+    equality constraints the reference itself uses potrf (:1173), and so does this factory."""
+    return KKTChol(G, dims, A, mnl, H, device, method="ldl2")
+
+
+def kkt_qr(G, dims, A=None, device=0):
+    """Drop-in for `misc.kkt_qr(G, dims, A)` (reference misc.py:1570-1699), the drivers' default for conelp with
+    second-order / semidefinite cones (coneprog.py:458-462): zero (1,1) block, equality constraints eliminated
+    with a Householder QR of A' (done once here), reduced system solved through  W^{-T} G Q2 = Q3 R3  instead of
+    the normal equations.  `factor(W)` takes no H / Df (as in the reference)."""
+    return KKTChol(G, dims, A, 0, None, device, method="qr")

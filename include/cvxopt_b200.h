@@ -84,6 +84,15 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims,
                     int space, int device);
 void cvxb_kkt_destroy(cvxb_kkt *k);
 
+/* Factorisation route of this factory, chosen once right after cvxb_kkt_create:
+ *   0  Cholesky of the reduced system           misc.kkt_chol / kkt_chol2   (misc.py:1213, :1352)  [default]
+ *   1  QR:  A' = [Q1 Q2][R1; 0] (Householder, once), W^{-T} G Q2 = Q3 R3 per factor (Cholesky-QR with
+ *      re-orthogonalisation, shifted when ill-conditioned)        misc.kkt_qr   (misc.py:1570-1699)
+ *   2  LDL' with Bunch-Kaufman pivoting of the 2x2 system [H + Gs'Gs, A'; A, 0]   misc.kkt_ldl2 (misc.py:1128-1210);
+ *      kktreg != 0 adds the reference's regularisation (misc.py:1096-1098 convention) to the diagonal.
+ * Route 1 accepts no H / Df (zero (1,1) block, conelp). */
+int cvxb_kkt_set_method(cvxb_kkt *k, int method, double kktreg);
+
 /* Make H (n x n, lower triangle significant) resident; later factor calls with
  * H == NULL and use_resident_H=1 add it.  coneqp passes the same P every
  * iteration (coneprog.py:1980-1981) — this avoids re-uploading n^2 doubles. */
@@ -153,6 +162,18 @@ int cvxb_sdot(const double *x, const double *y, const cvxb_dims *dims, double *r
  * Returns 1 if the eigensolver does not converge (non-finite input). */
 int cvxb_max_step(double *x, const cvxb_dims *dims, double *sigma, double *result,
                   int space);                                                /* :1052 */
+
+/* ---- Nesterov-Todd scaling itself: misc.compute_scaling (src/python/misc.py:250-419) and
+ * misc.update_scaling (:422-634) for every cone type.  `W` points at WRITABLE arrays laid out as in
+ * cvxb_scaling (the const qualifiers of that struct are cast away for these two calls): compute_scaling fills
+ * them, update_scaling updates them in place together with lmbda; update_scaling also overwrites s and z the
+ * way the reference does.  lmbda has mnl + ml + sum q + sum s entries.  's' blocks: Cholesky + one-sided Jacobi
+ * SVD on the device in place of lapack.potrf / lapack.gesvd; singular values in descending order.
+ * Returns info > 0 if an 's' block is not positive definite (ArithmeticError in the reference). */
+int cvxb_compute_scaling(const double *s, const double *z, double *lmbda, const cvxb_dims *dims,
+                         const cvxb_scaling *W, int space);
+int cvxb_update_scaling(const cvxb_scaling *W, double *lmbda, double *s, double *z,
+                        const cvxb_dims *dims, int space);
 
 /* ---- dense building blocks (the BLAS/LAPACK calls of the path, device pointers):
  * blas.syrk(trans='T') blas.c:3039 fused with the 'l' row scaling;

@@ -216,6 +216,68 @@ def _symL(x, m):
     return np.tril(X) + np.tril(X, -1).T
 
 
+def update_scaling(W, lmbda, s, z):
+    """misc.py:422-634.  In place on W (numpy arrays / lists of floats), lmbda, s, z.  The 's' components of s, z
+    hold the Cholesky factors Ls, Lz of the new iterates in the current scaling (zero above the diagonal)."""
+    mnl = len(W["dnl"]) if "dnl" in W else 0
+    ml = len(W["d"])
+    m = mnl + ml
+    s[:m] = np.sqrt(s[:m])                                            # :450-451
+    z[:m] = np.sqrt(z[:m])
+    if "dnl" in W:                                                    # :454-457
+        W["dnl"][:] = W["dnl"] * s[:mnl] / z[:mnl]
+        W["dnli"][:] = W["dnl"] ** -1
+    W["d"][:] = W["d"] * s[mnl:m] / z[mnl:m]                          # :458-460
+    W["di"][:] = W["d"] ** -1
+    lmbda[:m] = s[:m] * z[:m]                                         # :463-464
+    ind = m
+    for k in range(len(W["v"])):                                      # :504-573
+        v = W["v"][k]
+        mk = len(v)
+        aa = jnrm2(s, offset=ind, n=mk)
+        s[ind:ind + mk] *= 1.0 / aa
+        bb = jnrm2(z, offset=ind, n=mk)
+        z[ind:ind + mk] *= 1.0 / bb
+        sk, zk = s[ind:ind + mk], z[ind:ind + mk]
+        cc = math.sqrt((1.0 + float(np.dot(sk, zk))) / 2.0)
+        vs = float(np.dot(v, sk))
+        vz = jdot(v, z, offsety=ind, n=mk)
+        vq = (vs + vz) / 2.0 / cc
+        vu = vs - vz
+        lmbda[ind] = cc
+        wk0 = 2 * v[0] * vq - (sk[0] + zk[0]) / 2.0 / cc
+        dd = (v[0] * vu - sk[0] / 2.0 + zk[0] / 2.0) / (wk0 + 1.0)
+        lmbda[ind + 1: ind + mk] = v[1:] * (2.0 * (-dd * vq + 0.5 * vu))
+        lmbda[ind + 1: ind + mk] += 0.5 * (1.0 - dd / cc) * sk[1:]
+        lmbda[ind + 1: ind + mk] += 0.5 * (1.0 + dd / cc) * zk[1:]
+        lmbda[ind: ind + mk] *= math.sqrt(aa * bb)
+        v *= 2.0 * vq
+        v[0] -= sk[0] / 2.0 / cc
+        v[1:] += (0.5 / cc) * sk[1:]
+        v += (-0.5 / cc) * zk
+        v[0] += 1.0
+        v *= 1.0 / math.sqrt(2.0 * v[0])
+        W["beta"][k] *= math.sqrt(aa / bb)
+        ind += mk
+    ind2 = ind
+    for k in range(len(W["r"])):                                      # :592-634
+        r, rti = W["r"][k], W["rti"][k]
+        mk = r.shape[0]
+        Ls = s[ind2:ind2 + mk * mk].reshape(mk, mk, order="F").copy()
+        Lz = z[ind2:ind2 + mk * mk].reshape(mk, mk, order="F").copy()
+        r[:, :] = r @ Ls
+        rti[:, :] = rti @ Lz
+        U, sv, Vt = np.linalg.svd(Lz.T @ Ls)
+        lmbda[ind:ind + mk] = sv
+        s[ind2:ind2 + mk * mk] = U.reshape(-1, order="F")             # U in sk, V' in zk (:611-613)
+        z[ind2:ind2 + mk * mk] = Vt.reshape(-1, order="F")
+        a = 1.0 / np.sqrt(sv)
+        r[:, :] = (r @ Vt.T) * a[None, :]
+        rti[:, :] = (rti @ U) * a[None, :]
+        ind += mk
+        ind2 += mk * mk
+
+
 # --------------------------------------------------------------------------- kkt_chol
 class KktChol:
     """misc.kkt_chol (misc.py:1213-1349): factor(W, H, Df) -> solve(x, y, z).
