@@ -99,16 +99,102 @@ class QPBatch:
             pass
 
 
-def qp_batch(P, q, G, h, device=0, **options):
-    """Solve B independent dense QPs on one GPU.  P (B,n,n), q (B,n), G (B,m,n), h (B,m)."""
+def _split(n, parts):
+    base, extra = divmod(n, parts)
+    out, lo = [], 0
+    for r in range(parts):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+class QPBatchGroup:
+    """`nsub` QPBatch objects over interleaved slices of one batch, solved CONCURRENTLY on their own CUDA streams
+    (one host thread each; ctypes releases the GIL inside the library calls).  A lock-step batch alternates
+    throughput-bound phases (batched SYRK / GEMV) with latency-bound ones (the chain of diagonal-block
+    factorisations, the flag-chained triangular solves); with two or more sub-batches in flight the GPU runs one
+    sub-batch's latency-bound phase under another's throughput-bound phase, and a sub-batch stops iterating as soon
+    as ITS slowest problem is done.  Interleaved slices (problem i -> sub-batch i mod nsub) spread hard and easy
+    problems evenly."""
+
+    def __init__(self, nprob, n, m, device=0, nsub=None):
+        if nsub is None:
+            nsub = int(__import__("os").environ.get("CVXB_BATCH_NSUB", "0")) or (4 if nprob >= 16 else 1)
+        self.nsub = max(1, min(int(nsub), nprob))
+        self.B, self.n, self.m = int(nprob), int(n), int(m)
+        self.idx = [np.arange(r, self.B, self.nsub) for r in range(self.nsub)]
+        self.parts = [QPBatch(len(ix), n, m, device) for ix in self.idx]
+
+    def load_ptr_sliced(self, loader):
+        """loader(part_index, indices, QPBatch) loads one sub-batch (device-resident callers)"""
+        for r, (ix, b) in enumerate(zip(self.idx, self.parts)):
+            loader(r, ix, b)
+
+    def load(self, P, q, G, h):
+        P, q, G, h = (np.asarray(a) for a in (P, q, G, h))
+        for ix, b in zip(self.idx, self.parts):
+            b.load(P[ix], q[ix], G[ix], h[ix])
+
+    def solve(self, **options):
+        if self.nsub == 1:
+            self.parts[0].solve(**options)
+            return
+        import threading
+        errs = []
+
+        def run(b):
+            try:
+                b.solve(**options)
+            except BaseException as e:      # noqa: BLE001  re-raised on the calling thread
+                errs.append(e)
+        th = [threading.Thread(target=run, args=(b,)) for b in self.parts]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def results(self):
+        B, n, m = self.B, self.n, self.m
+        out = {"x": np.zeros((B, n)), "s": np.zeros((B, m)), "z": np.zeros((B, m)),
+               "status_code": np.zeros(B, dtype=np.int32), "iterations": np.zeros(B, dtype=np.int32),
+               "primal objective": np.zeros(B), "dual objective": np.zeros(B)}
+        for ix, b in zip(self.idx, self.parts):
+            r = b.results()
+            for key in out:
+                out[key][ix] = r[key]
+        out["status"] = [STATUS[int(k)] for k in out["status_code"]]
+        return out
+
+    def stats(self):
+        st = [b.stats() for b in self.parts]
+        return {"solve_ms": max(s["solve_ms"] for s in st),
+                "lockstep_iterations": max(s["lockstep_iterations"] for s in st),
+                "lockstep_iterations_per_subbatch": [s["lockstep_iterations"] for s in st],
+                "syrk_path": st[0]["syrk_path"], "nsub": self.nsub}
+
+    def close(self):
+        for b in self.parts:
+            b.close()
+
+
+def qp_batch(P, q, G, h, device=0, nsub=None, **options):
+    """Solve B independent dense QPs on one GPU.  P (B,n,n), q (B,n), G (B,m,n), h (B,m).
+    nsub: number of concurrently solved sub-batches (QPBatchGroup); default 4 (1 for tiny batches)."""
     P = np.asarray(P)
     G = np.asarray(G)
-    b = QPBatch(P.shape[0], P.shape[1], G.shape[1], device)
+    b = QPBatchGroup(P.shape[0], P.shape[1], G.shape[1], device, nsub)
     try:
         b.load(P, q, G, h)
+        import time
+        t0 = time.perf_counter()
         b.solve(**options)
+        wall = (time.perf_counter() - t0) * 1e3
         out = b.results()
         out.update(b.stats())
+        out["solve_wall_ms"] = wall
         return out
     finally:
         b.close()
@@ -149,7 +235,7 @@ def _p2p(ops):
 
 
 def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interleaved", timings=None,
-                         **options):
+                         nsub=None, **options):
     """Rank 0 passes the full batch (other ranks pass None); every rank returns its shard's results and
     rank 0 additionally gets the gathered batch, in the original problem order, under key 'all'.
 
@@ -205,7 +291,7 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
     # ---- setup (not data path): this rank's batch object = its device allocations ----
     local_dev = torch.cuda.current_device() if on_gpu else 0
     clk.start("setup_ms")
-    bobj = QPBatch(k, n, m, local_dev) if (solver is None and k) else None
+    bobj = QPBatchGroup(k, n, m, local_dev, nsub) if (solver is None and k) else None
     clk.stop()
 
     # ---- scatter ----
@@ -253,19 +339,33 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
         if k:
             b = bobj
             try:
-                # shards are already in device memory: straight into the batch, no host bounce
-                b.load_ptr(shard[0].data_ptr(), shard[1].data_ptr(), shard[2].data_ptr(), shard[3].data_ptr(),
-                           _lib.DEVICE)
+                # shards are already in device memory: straight into the sub-batches, no host bounce
+                keepalive = []
+
+                def loader(r, ix, part):
+                    it = torch.from_numpy(ix).to(dev)
+                    sl = [t.index_select(0, it) for t in shard] if b.nsub > 1 else shard
+                    keepalive.append(sl)
+                    part.load_ptr(sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(), sl[3].data_ptr(), _lib.DEVICE)
+                b.load_ptr_sliced(loader)
+                del keepalive
                 b.solve(**options)
-                status = np.zeros(k, dtype=np.int32); iters = np.zeros(k, dtype=np.int32)
-                pobj, dobj = np.zeros(k), np.zeros(k)
-                lib = b._lib
-                _lib.check(lib.cvxb_batch_results(b._h, xs.data_ptr(), ss.data_ptr(), zs.data_ptr(), None, None,
-                                                  None, None, _lib.DEVICE), "batch_results")
-                _lib.check(lib.cvxb_batch_results(b._h, None, None, None, status.ctypes.data, iters.ctypes.data,
-                                                  pobj.ctypes.data, dobj.ctypes.data, _lib.HOST), "batch_results")
-                sc = torch.from_numpy(np.stack([status.astype(np.float64), iters.astype(np.float64), pobj, dobj],
-                                               axis=1)).to(dev)
+                for ix, part in zip(b.idx, b.parts):
+                    kk = len(ix)
+                    it = torch.from_numpy(ix).to(dev)
+                    px = torch.empty((kk, n), dtype=f64, device=dev)
+                    ps = torch.empty((kk, m), dtype=f64, device=dev)
+                    pz = torch.empty((kk, m), dtype=f64, device=dev)
+                    status = np.zeros(kk, dtype=np.int32); iters = np.zeros(kk, dtype=np.int32)
+                    pobj, dobj = np.zeros(kk), np.zeros(kk)
+                    lib = part._lib
+                    _lib.check(lib.cvxb_batch_results(part._h, px.data_ptr(), ps.data_ptr(), pz.data_ptr(), None, None,
+                                                      None, None, _lib.DEVICE), "batch_results")
+                    _lib.check(lib.cvxb_batch_results(part._h, None, None, None, status.ctypes.data, iters.ctypes.data,
+                                                      pobj.ctypes.data, dobj.ctypes.data, _lib.HOST), "batch_results")
+                    xs.index_copy_(0, it, px); ss.index_copy_(0, it, ps); zs.index_copy_(0, it, pz)
+                    sc.index_copy_(0, it, torch.from_numpy(np.stack(
+                        [status.astype(np.float64), iters.astype(np.float64), pobj, dobj], axis=1)).to(dev))
                 stats = b.stats()
             finally:
                 b.close()

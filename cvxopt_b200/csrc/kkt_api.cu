@@ -588,6 +588,7 @@ int cvxb_kkt_trace(cvxb_kkt *k, unsigned long long *out, int nsteps) {
     return 0;
 }
 int cvxb_kkt_syrk_path(cvxb_kkt *k) { return k ? k->syrk_path : CVXB_E_ARG; }
+int cvxb_kkt_qr_passes(cvxb_kkt *k) { return (k && k->method == 1) ? kkt_qr_passes(k) : CVXB_E_ARG; }
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3) {
     if (!k || !ms3) return CVXB_E_ARG;
     ms3[0] = k->br[1]; ms3[1] = k->br[2]; ms3[2] = k->br[0];

@@ -73,6 +73,7 @@ int kkt_unpack_z(cvxb_kkt *k, double *zd);           // z := unpack(k->bzp)
 int kkt_qr_factor(cvxb_kkt *k, const cvxb_scaling *W, int space);
 int kkt_qr_solve(cvxb_kkt *k, double *x, double *y, double *z, int space);
 int kkt_qr_setup(cvxb_kkt *k);
+int kkt_qr_passes(const cvxb_kkt *k);
 // LDL' route: Kmat holds S (lower) on entry of factor; info (k->cw.d_info) = first exactly-zero pivot, 1-based
 int kkt_ldl_factor(cvxb_kkt *k);
 int kkt_ldl_solve(cvxb_kkt *k, double *xd, double *yd);        // device vectors, in place

@@ -289,6 +289,8 @@ int kkt_qr_factor(cvxb_kkt *k, const cvxb_scaling *Wp, int space) {
     return 0;
 }
 
+int kkt_qr_passes(const cvxb_kkt *k) { return k->ext ? static_cast<const QrState *>(k->ext)->npass : 0; }
+
 int kkt_qr_solve(cvxb_kkt *k, double *x, double *y, double *z, int space) {
     QrState *q = static_cast<QrState *>(k->ext);
     const ConeLayout &c = k->cone;

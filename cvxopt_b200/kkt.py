@@ -273,6 +273,10 @@ class KKTChol:
         """'none' | 'dmma' | 'int8': the kernel that computed the last factor's 'l'-row SYRK"""
         return ("none", "dmma", "int8")[self._lib.cvxb_kkt_syrk_path(self._h)]
 
+    def qr_passes(self):
+        """QR route: 2 = Cholesky-QR with re-orthogonalisation, 3 = the shifted variant took over"""
+        return self._lib.cvxb_kkt_qr_passes(self._h)
+
     def get_L(self):
         L = np.zeros((self.n, self.n), order="F")
         _lib.check(self._lib.cvxb_kkt_get_L(self._h, L.ctypes.data, max(1, self.n)), "get_L")

@@ -126,6 +126,8 @@ int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3);
  * (mma.sync.m8n8k4.f64), 2 int8 slices on tcgen05.mma kind::i8 (large problems; CVXB_OZAKI=0 disables,
  * falls back to 1 when the slice workspace does not fit in device memory) */
 int cvxb_kkt_syrk_path(cvxb_kkt *k);
+/* QR route: Cholesky-QR passes of the last factor: 2 (plain, re-orthogonalised) or 3 (shifted, ill-conditioned) */
+int cvxb_kkt_qr_passes(cvxb_kkt *k);
 
 /* device-resident G / P operators for the function-valued G(x,y,alpha,beta,trans)
  * / P(x,y,alpha,beta) protocol of coneprog (coneprog.py:1682-1711):

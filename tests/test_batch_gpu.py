@@ -64,3 +64,17 @@ def test_batch_rank_deficient_raises():
     h = np.ones((1, m))
     with pytest.raises(ValueError):
         cvxopt_b200.qp_batch(P, q, G, h)
+
+
+def test_concurrent_subbatches_match_single_batch():
+    """QPBatchGroup: interleaved sub-batches solved concurrently on their own streams give the same per-problem
+    results as one lock-step batch"""
+    import cvxopt_b200
+    P, q, G, h = make_batch(7, 60, 130, seed0=40)
+    one = cvxopt_b200.qp_batch(P, q, G, h, nsub=1)
+    three = cvxopt_b200.qp_batch(P, q, G, h, nsub=3)
+    assert three["nsub"] == 3 and one["nsub"] == 1
+    assert list(one["iterations"]) == list(three["iterations"])
+    assert all(s == "optimal" for s in three["status"])
+    np.testing.assert_allclose(three["x"], one["x"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(three["primal objective"], one["primal objective"], rtol=1e-12)

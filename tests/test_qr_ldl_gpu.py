@@ -79,6 +79,7 @@ def test_kkt_qr_matches_reference(ref, dims, n, p):
     f_ref = misc.kkt_qr(Gm, dims, Am)(W)
     fac = cvxopt_b200.kkt_qr(Gm, dims, Am if p else None)
     f_gpu = fac(W)
+    assert fac.qr_passes() == 2
     _compare(f_ref, f_gpu, dims, n, p, rng, 1e-10)
     fac.close()
 
@@ -98,6 +99,7 @@ def test_kkt_qr_ill_conditioned_takes_the_shifted_path(ref):
     f_ref = misc.kkt_qr(Gm, dims, matrix(0.0, (0, n)))(W)
     fac = cvxopt_b200.kkt_qr(Gm, dims, None)
     f_gpu = fac(W)
+    assert fac.qr_passes() == 3
     _compare(f_ref, f_gpu, dims, n, p, rng, 1e-5)
     fac.close()
 
