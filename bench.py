@@ -183,6 +183,58 @@ def run_e2e_driver(n, m, seed, device):
     return out
 
 
+def run_e2e_cones(device):
+    """BASELINE configs 3 and 5 as whole solves through the UNMODIFIED reference driver (solvers.conelp from
+    oracle/_ref) with every device piece plugged in: kktsolver (Cholesky route), and misc.compute_scaling /
+    misc.update_scaling swapped for the device versions (NT scaling of the 'q' / 's' cones, Jacobi SVD).
+    Reference numbers beside it: tests/golden/config_runs.json (the reference's own kktsolver='chol' runs)."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "cvxopt")):
+        return {"unavailable": "oracle/_ref not built"}
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cvxopt_b200
+    from cvxopt import matrix, misc, solvers
+    from problems import cone_lp
+    solvers.options["show_progress"] = False
+    try:
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", "config_runs.json")))
+    except Exception:       # noqa: BLE001
+        gold = {}
+    out = {}
+    for name, n, dims in (("cfg3_socp", 2048, {"l": 0, "q": [64] * 64, "s": []}),
+                          ("cfg5_sdp", 512, {"l": 0, "q": [], "s": [512]})):
+        c, G, h = cone_lp(n, dims, seed=11)
+        cm, Gm, hm = matrix(c), matrix(G), matrix(h)
+        f = cvxopt_b200.kkt_chol(Gm, dims, device=device)
+        res = {}
+        for mode in ("kktsolver", "kktsolver_and_device_scaling"):
+            saved = misc.compute_scaling, misc.update_scaling
+            if mode != "kktsolver":
+                misc.compute_scaling = lambda s, z, lmbda, dims, mnl=None: cvxopt_b200.scaling.compute_scaling(
+                    s, z, lmbda, dims, mnl, new_matrix=lambda r, cc: matrix(0.0, (r, cc)))
+                misc.update_scaling = cvxopt_b200.scaling.update_scaling
+            try:
+                f.reset()
+                t0 = time.perf_counter()
+                sol = solvers.conelp(cm, Gm, hm, dims, kktsolver=lambda W: f(W))
+                dt = time.perf_counter() - t0
+            finally:
+                misc.compute_scaling, misc.update_scaling = saved
+            res[mode] = {"seconds": dt, "iterations": int(sol["iterations"]), "status": sol["status"],
+                         "iters_per_s": (sol["iterations"] + 1) / dt,
+                         "primal_objective": float(sol["primal objective"])}
+        f.close()
+        g = gold.get(name.split("_")[0])
+        if g:
+            res["reference_cpu_golden"] = {"seconds": g["seconds"], "iterations": g["iterations"],
+                                           "primal_objective": g["primal objective"],
+                                           "note": "reference kktsolver='chol' on the 8-core build container"}
+        out[name] = res
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -584,6 +636,10 @@ def main():
                     extras["e2e_driver"] = run_e2e_driver(4096, 8192, args.seed, local_rank)
                 except Exception as exc:    # noqa: BLE001
                     extras["e2e_driver"] = {"error": repr(exc)[:300]}
+                try:
+                    extras["e2e_cones"] = run_e2e_cones(local_rank)
+                except Exception as exc:    # noqa: BLE001
+                    extras["e2e_cones"] = {"error": repr(exc)[:300]}
     if rank == 0:
         out.update(extras)
         print(json.dumps(out))

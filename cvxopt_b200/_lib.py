@@ -41,6 +41,7 @@ _SIGS = {
     "cvxb_kkt_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(Dims),
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "cvxb_kkt_destroy": (None, [C.c_void_p]),
+    "cvxb_kkt_reset": (C.c_int, [C.c_void_p]),
     "cvxb_kkt_set_method": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "cvxb_kkt_set_H": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "cvxb_kkt_factor": (C.c_int, [C.c_void_p, C.POINTER(Scaling), C.c_void_p, C.c_int,

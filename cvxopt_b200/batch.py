@@ -120,7 +120,10 @@ class QPBatchGroup:
 
     def __init__(self, nprob, n, m, device=0, nsub=None):
         if nsub is None:
-            nsub = int(__import__("os").environ.get("CVXB_BATCH_NSUB", "0")) or (4 if nprob >= 16 else 1)
+            # measured on B200 (profiles/r02h_batch_nsub.txt, n=512 m=1024): 512 problems 148 -> 142 ms with 2
+            # sub-batches; 64 problems 25.0 -> 21.3 ms with 8
+            nsub = int(__import__("os").environ.get("CVXB_BATCH_NSUB", "0")) or (
+                2 if nprob >= 256 else (max(1, min(8, nprob // 8)) if nprob >= 16 else 1))
         self.nsub = max(1, min(int(nsub), nprob))
         self.B, self.n, self.m = int(nprob), int(n), int(m)
         self.idx = [np.arange(r, self.B, self.nsub) for r in range(self.nsub)]

@@ -365,6 +365,10 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
 // forward:  L x = b ;  backward: L' x = b.   In place on b.  One CTA per 128-row block.
 // flags[i] == epoch  <=>  x_i is final in b.
 //
+// Forward-progress assumption: CTA `bi` spins on the flags of the blocks it depends on, which are produced by
+// CTAs with a SMALLER blockIdx.x (forward; the backward kernel reverses the block order so the same holds).  The
+// hardware dispatches the CTAs of a grid in ascending linear block index, so a spinning CTA's producers are always
+// resident or already finished; with at most ceil(n/128) CTAs per problem the whole grid is usually co-resident.
 // CTA `bi` streams its block row (forward) / block column (backward) of L through a
 // cp.async ring of 128x32 chunks that runs ahead of the dependency chain (L is static,
 // only x arrives late), keeps inv(L_ii) in registers, and waits on the flag of block j
@@ -624,12 +628,15 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
     //                   column 2g+2 below its diagonal tile;  bulk R with K = 2 NB on block columns >= 2g+3.
     // A K = 128 update keeps the DMMA pipe 63 % busy (prologue + read-modify-write epilogue per 8 k steps,
     // profiles/r01e); K = 256 halves the C traffic and the per-tile overhead of the bulk flops.
+    // CVXB_CHOL_PAIR = 0 off (default), 1 every step, k >= 2: the first k (even) steps only — the pair form helps
+    // where the bulk update sets the pace (large trailing matrix) and hurts once the diagonal chain does.
     static int pair_mode = -1;
     if (pair_mode < 0) {
         const char *e = getenv("CVXB_CHOL_PAIR");
-        pair_mode = (e && e[0] == '1') ? 1 : 0;
+        pair_mode = e ? atoi(e) : 0;
+        if (pair_mode < 0) pair_mode = 0;
     }
-    const bool pair = pair_mode == 1;
+    const int pair_limit = pair_mode == 1 ? (1 << 30) : (pair_mode & ~1);
     int last_r = -1;                       // last step that recorded ev_r
     int prev_r = -1;                       // the one before
     for (int jb = 0; jb < nblk; ++jb) {
@@ -639,6 +646,8 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         double *Ajj = A + j + (long long)j * lda;
         double *invj = inv + (long long)jb * NB * NB;
         double *invTj = inv + (long long)(nblk + jb) * NB * NB;
+        const bool pair = jb < pair_limit;
+        const bool pair_prev = (jb - 1) < pair_limit;
         const bool odd = pair && (jb & 1);
         // Group buffer of this step.  Its row r is global row R0 + r, R0 = first row below the EVEN panel's
         // diagonal block, for both panels of the pair: the odd panel's TRSM result therefore sits at column
@@ -669,7 +678,7 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             if (jb == 0) return 0;
             const int jp = j - NB, mp = n - j;
             const int pb = jb - 1;
-            const double *src = pair ? w.panel[(pb >> 1) & 1] + ((pb & 1) ? (long long)NB * ldw + NB : 0) : w.panel[pb & 1];
+            const double *src = pair_prev ? w.panel[(pb >> 1) & 1] + ((pb & 1) ? (long long)NB * ldw + NB : 0) : w.panel[pb & 1];
             CVXB_CUDA(cudaMemcpy2DAsync(A + j + (long long)jp * lda, (size_t)lda * sizeof(double),
                                         src, (size_t)ldw * sizeof(double),
                                         (size_t)mp * sizeof(double), NB, cudaMemcpyDeviceToDevice, T));
@@ -686,6 +695,7 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_dg[jb], 0));
         // the group buffer about to be overwritten was read by the bulk update two groups (steps) ago
         if (!odd && prev_r >= 0) CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_r[prev_r], 0));
+        if (!pair && pair_prev && last_r >= 0) CVXB_CUDA(cudaStreamWaitEvent(T, w.ev_r[last_r], 0));   // mode switch
         {
             GemmDesc g;
             g.M = m; g.N = wj; g.K = wj;

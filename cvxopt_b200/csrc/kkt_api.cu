@@ -290,6 +290,16 @@ int cvxb_kkt_set_method(cvxb_kkt *k, int method, double kktreg) {
     return CVXB_E_ARG;
 }
 
+int cvxb_kkt_reset(cvxb_kkt *k) {
+    if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
+    // a new solver run on the same factory: the "S was singular on the first factorisation -> S + A'A from then
+    // on" decision (misc.py:1433-1447) belongs to ONE run of the driver
+    k->singular = false;
+    k->first_factor = true;
+    k->factored = false;
+    return 0;
+}
+
 int cvxb_kkt_set_H(cvxb_kkt *k, const double *H, int ldh, int space) {
     if (!k) { set_error("kkt is NULL"); return CVXB_E_ARG; }
     CVXB_CUDA(cudaSetDevice(k->device));

@@ -153,6 +153,11 @@ class KKTChol:
         if H is not None:
             self.set_H(H)
 
+    def reset(self):
+        """start a new solver run on this factory: the reference builds a fresh kkt_chol2 closure per run, whose
+        `F['firstcall']` / `F['singular']` state (misc.py:1395-1447) this clears"""
+        _lib.check(self._lib.cvxb_kkt_reset(self._h), "reset")
+
     # -- resident H ---------------------------------------------------------
     def set_H(self, H):
         Hm = _mat(H, "H")

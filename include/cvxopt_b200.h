@@ -93,6 +93,10 @@ void cvxb_kkt_destroy(cvxb_kkt *k);
  * Route 1 accepts no H / Df (zero (1,1) block, conelp). */
 int cvxb_kkt_set_method(cvxb_kkt *k, int method, double kktreg);
 
+/* Start a new solver run on the same factory (G, A, H stay resident): forgets the first-factorisation state
+ * ("S singular on the first call -> S + A'A for the rest of the run", misc.py:1433-1447). */
+int cvxb_kkt_reset(cvxb_kkt *k);
+
 /* Make H (n x n, lower triangle significant) resident; later factor calls with
  * H == NULL and use_resident_H=1 add it.  coneqp passes the same P every
  * iteration (coneprog.py:1980-1981) — this avoids re-uploading n^2 doubles. */
