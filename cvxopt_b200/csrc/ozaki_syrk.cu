@@ -61,6 +61,10 @@ struct OzParams {
     int pd0[OZ_MAXPASS], pd1[OZ_MAXPASS];
     const unsigned int *tiles; // (I << 16) | J per CTA, in launch order
     unsigned int *dbg;         // optional progress words (mapped host memory) or nullptr
+    // split-K launch of the tail wave: CTA b works on tile b / nchunk over k steps [c*kper, (c+1)*kper), c = b % nchunk,
+    // and writes its 128 x 128 partial (tile-local, column-major) to part + b * 128*128; oz_tail_reduce_kernel sums them
+    int nchunk, kper;
+    double *part;
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -178,8 +182,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
              *acc_empty = bars + 2 * OZ_MAXST + 1;
 
     // lower-triangular tile (I >= J) of this CTA
-    const unsigned int tl = p.tiles[blockIdx.x];
+    const bool split = p.nchunk > 1;
+    const unsigned int tl = p.tiles[split ? blockIdx.x / p.nchunk : blockIdx.x];
     const int I = (int)(tl >> 16), J = (int)(tl & 0xFFFFu);
+    const int kb = split ? (int)(blockIdx.x % p.nchunk) * p.kper : 0;
+    const int ke = split ? min(p.nk, kb + p.kper) : p.nk;
 
     if (tid == 0) {
         for (int s = 0; s < OZ_MAXST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
 
     const int S = p.S;
     const int npass = p.npass;
-    const int nrange = (p.nk + OZ_KRANGE - 1) / OZ_KRANGE;
+    const int nrange = (ke - kb + OZ_KRANGE - 1) / OZ_KRANGE;
     // Stage geometry of a pass: nS slices of A then nS slices of B per k step; the ring is cut into
     // as many such stages as fit (deeper prefetch for the passes that need few slices).
 
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
             // ===== producer: one bulk copy per operand per k step =====
             uint32_t filled = 0, epar = 0;               // per stage: ever filled / parity of its last release
             for (int rg = 0; rg < nrange; ++rg) {
-                const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
+                const int k0 = kb + rg * OZ_KRANGE, k1 = min(ke, k0 + OZ_KRANGE);
                 for (int ps = 0; ps < npass; ++ps) {
                     const int nS = min(S, p.pd1[ps] + 1);
                     const int nst = min(OZ_MAXST, OZ_RING / (2 * nS));
@@ -242,7 +249,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
         int g = 0;                                   // global pass counter (for the accumulator barriers)
         const uint32_t sbase = smem_u32(smem);
         for (int rg = 0; rg < nrange; ++rg) {
-            const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
+            const int k0 = kb + rg * OZ_KRANGE, k1 = min(ke, k0 + OZ_KRANGE);
             for (int ps = 0; ps < npass; ++ps, ++g) {
                 const int d0 = p.pd0[ps], d1 = p.pd1[ps];
                 const int nS = min(S, d1 + 1);
@@ -322,7 +329,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
                         if (nlev > 1) v = fma(v, 128.0, (double)(int)r[1][c]);
                         if (nlev > 2) v = fma(v, 128.0, (double)(int)r[2][c]);
                         if (nlev > 3) v = fma(v, 128.0, (double)(int)r[3][c]);
-                        if (row_ok && col < p.n && col <= row) {
+                        if (split) {
+                            v = (col < p.n) ? (v * lsc) * rsc * p.cs[col] : 0.0;
+                            double *dst = p.part + (size_t)blockIdx.x * (OZ_T * OZ_T) + (quad * 32 + lane) + (size_t)(c0 + c) * OZ_T;
+                            if (!first) v += *dst;
+                            *dst = v;
+                        } else if (row_ok && col < p.n && col <= row) {
                             v = (v * lsc) * rsc * p.cs[col];
                             double *dst = p.C + row + (size_t)col * p.ldc;
                             if (first) v += (p.D ? p.beta * p.D[row + (size_t)col * p.ldd] : 0.0);
@@ -627,6 +639,22 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
     }
 }
 
+// C tile = beta * D + sum of the nchunk partial tiles of the split-K tail launch (fixed order: deterministic)
+__global__ void oz_tail_reduce_kernel(OzParams p, int ntail) {
+    const int t = blockIdx.y;
+    const unsigned int tl = p.tiles[t];
+    const int I = (int)(tl >> 16), J = (int)(tl & 0xFFFFu);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= OZ_T * OZ_T) return;
+    const int r = e % OZ_T, c = e / OZ_T;
+    const int row = I * OZ_T + r, col = J * OZ_T + c;
+    if (row >= p.n || col >= p.n || col > row) return;
+    double v = p.D ? p.beta * p.D[row + (size_t)col * p.ldd] : 0.0;
+    const double *src = p.part + (size_t)t * p.nchunk * (OZ_T * OZ_T) + e;
+    for (int ch = 0; ch < p.nchunk; ++ch) v += src[(size_t)ch * (OZ_T * OZ_T)];
+    p.C[row + (size_t)col * p.ldc] = v;
+}
+
 // amax[j] = max_k |d[k] * A[k,j]|  ->  cs[j] = 2^e_j, sinv[j] = 64 * 2^-e_j
 __global__ void oz_colscale_kernel(int m, int n, const double *A, long long lda, const double *d, double *cs, double *sinv) {
     __shared__ double sh[32];
@@ -737,7 +765,8 @@ static void oz_choose_groups(int S, int *npass, int *pd0, int *pd1) {
 
 size_t ozaki_workspace_bytes(int n, int m, int S) {
     const size_t nblk = (n + OZ_T - 1) / OZ_T, nk = std::max(1, (m + OZ_KS - 1) / OZ_KS);
-    return nblk * nk * (size_t)S * OZ_UNIT + 2 * (size_t)n * sizeof(double) + nblk * (nblk + 1) / 2 * sizeof(unsigned int) + 1024;
+    return nblk * nk * (size_t)S * OZ_UNIT + 2 * (size_t)n * sizeof(double) + nblk * (nblk + 1) / 2 * sizeof(unsigned int) + 1024
+           + (size_t)kNumSMs * OZ_T * OZ_T * sizeof(double) + 256;         // partial tiles of the split-K tail wave
 }
 
 // C(lower) = A' diag(d)^2 A + beta * D.  A: m x n (lda), d: m (or nullptr).  work: ozaki_workspace_bytes.
@@ -812,7 +841,29 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
         cfg.attrs = at; cfg.numAttrs = 1;
         CVXB_CUDA(cudaLaunchKernelEx(&cfg, oz_mma2_kernel, p));
     } else {
-        oz_mma_kernel<<<(unsigned)tiles, OZ_THREADS, OZ_SMEM, st>>>(p);
+        // The last, partial wave of tiles (2080 = 14 x 148 + 8 at n = 8192) would leave most SMs idle for a whole
+        // tile time: its tiles are split along K over all SMs (partials + ordered reduce).  CVXB_OZ_TAIL=0 disables.
+        p.nchunk = 1; p.kper = nk; p.part = nullptr;
+        long long tmain = tiles;
+        int ntail = (int)(tiles % kNumSMs), nchunk = 1;
+        static int tail_on = -1;
+        if (tail_on < 0) { const char *e = getenv("CVXB_OZ_TAIL"); tail_on = (e && e[0] == '0') ? 0 : 1; }
+        if (tail_on && tiles > kNumSMs && ntail > 0 && ntail <= kNumSMs / 2) {
+            nchunk = std::min(kNumSMs / ntail, nk);
+            if (nchunk >= 2) tmain = tiles - ntail; else nchunk = 1;
+        }
+        if (tmain > 0) oz_mma_kernel<<<(unsigned)tmain, OZ_THREADS, OZ_SMEM, st>>>(p);
+        if (nchunk >= 2) {
+            OzParams pt = p;
+            pt.tiles = dtiles + tmain;
+            pt.nchunk = nchunk;
+            pt.kper = (nk + nchunk - 1) / nchunk;
+            pt.nchunk = (nk + pt.kper - 1) / pt.kper;                 // no empty chunk
+            pt.part = reinterpret_cast<double *>(((uintptr_t)(Q + (size_t)nblk * nk * S * OZ_UNIT) + 255) & ~uintptr_t(255));
+            oz_mma_kernel<<<(unsigned)(ntail * pt.nchunk), OZ_THREADS, OZ_SMEM, st>>>(pt);
+            oz_tail_reduce_kernel<<<dim3(OZ_T * OZ_T / 256, ntail), 256, 0, st>>>(pt, ntail);
+            count_launch(2);
+        }
     }
     count_launch();
     CVXB_LAUNCH_CHECK();

@@ -10,11 +10,11 @@ import kkt_oracle as ko
 from problems import cone_dim, cone_lp, random_scaling
 
 
-def run(name, dims, n, check):
+def run(name, dims, n, check, route="chol"):
     K = cone_dim(dims)
     c, G, h = cone_lp(n, dims, seed=11)
     W, _ = random_scaling(dims, seed=5)
-    fac = cvxopt_b200.kkt_chol(G, dims)
+    fac = cvxopt_b200.kkt_qr(G, dims) if route == "qr" else cvxopt_b200.kkt_chol(G, dims)
     rng = np.random.Generator(np.random.PCG64(1))
     solve = fac(W)
     ts = []
@@ -32,7 +32,7 @@ def run(name, dims, n, check):
     _, _, _, _, kp = ko.cone_sizes(dims)
     f_cong = sum(3.0 * s ** 3 * n for s in dims["s"])
     f_fac = float(n) * n * kp + n ** 3 / 3.0 + f_cong
-    out = {"config": name, "n": n, "cdim": K, "cdim_pckd": kp, "factor_ms_wall": tf, "solve_ms_wall": tsol,
+    out = {"config": name, "route": route, "n": n, "cdim": K, "cdim_pckd": kp, "factor_ms_wall": tf, "solve_ms_wall": tsol,
            "factor_ms_dev": ts[-1][2][0], "solve_ms_dev": ts[-1][2][1], "breakdown": ts[-1][3],
            "factor_tflops": f_fac / (ts[-1][2][0] * 1e-3) * 1e-12}
     if check:
@@ -49,7 +49,11 @@ def run(name, dims, n, check):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["3", "5"]
+    which = sys.argv[1:] or ["2", "3", "3qr", "5"]
+    if "2" in which:
+        run("2: QP n=4096, l=8192 (KKT step without P)", {"l": 8192, "q": [], "s": []}, 4096, True)
+    if "3qr" in which:
+        run("3: SOCP n=2048, 64 x q64", {"l": 0, "q": [64] * 64, "s": []}, 2048, False, route="qr")
     if "3" in which:
         run("3: SOCP n=2048, 64 x q64", {"l": 0, "q": [64] * 64, "s": []}, 2048, True)
     if "5" in which:
