@@ -6,9 +6,10 @@ the host-side mirror of the reference's kktsolver / misc_solvers interface.
 from ._lib import load, exported_symbols, LIB_PATH  # noqa: F401
 from .kkt import kkt_chol, kkt_chol2, kkt_ldl2, kkt_qr, KKTChol, cp_kktsolver, cpl_kktsolver  # noqa: F401
 from . import scaling  # noqa: F401
+from .conelp import conelp  # noqa: F401
 from .batch import QPBatch, QPBatchGroup, qp_batch, qp_batch_distributed, shard_bounds, shard_indices  # noqa: F401
 
-__all__ = ["kkt_chol", "kkt_chol2", "kkt_ldl2", "kkt_qr", "KKTChol", "cp_kktsolver", "cpl_kktsolver", "QPBatch", "qp_batch", "qp_batch_distributed", "load",
+__all__ = ["kkt_chol", "kkt_chol2", "kkt_ldl2", "kkt_qr", "KKTChol", "cp_kktsolver", "cpl_kktsolver", "QPBatch", "qp_batch", "conelp", "qp_batch_distributed", "load",
            "device_count", "launch_count"]
 
 
