@@ -184,8 +184,9 @@ def run_e2e_driver(n, m, seed, device):
 
 
 def run_e2e_cones(device):
-    """BASELINE configs 3 and 5 as whole solves through the UNMODIFIED reference driver (solvers.conelp from
-    oracle/_ref) with every device piece plugged in: kktsolver (Cholesky route), and misc.compute_scaling /
+    """BASELINE configs 3 and 5 as whole solves: (a) through the UNMODIFIED reference driver (solvers.conelp from
+    oracle/_ref) with every device piece plugged in, (b) through the device-resident restatement cvxopt_b200.conelp.
+    (a): kktsolver (Cholesky route), and misc.compute_scaling /
     misc.update_scaling swapped for the device versions (NT scaling of the 'q' / 's' cones, Jacobi SVD).
     Reference numbers beside it: tests/golden/config_runs.json (the reference's own kktsolver='chol' runs)."""
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
@@ -226,6 +227,15 @@ def run_e2e_cones(device):
                          "iters_per_s": (sol["iterations"] + 1) / dt,
                          "primal_objective": float(sol["primal objective"])}
         f.close()
+        # the device-resident driver (cvxopt_b200.conelp): all iterates in HBM, scalars only over PCIe; the time
+        # includes uploading G (1.07 GB for config 5)
+        cvxopt_b200.conelp(c, G, h, dims, maxiters=2)            # warm-up: first launches of its kernels
+        t0 = time.perf_counter()
+        sol = cvxopt_b200.conelp(c, G, h, dims)
+        dt = time.perf_counter() - t0
+        res["device_conelp"] = {"seconds": dt, "iterations": int(sol["iterations"]), "status": sol["status"],
+                                "iters_per_s": (sol["iterations"] + 1) / dt,
+                                "primal_objective": float(sol["primal objective"])}
         g = gold.get(name.split("_")[0])
         if g:
             res["reference_cpu_golden"] = {"seconds": g["seconds"], "iterations": g["iterations"],

@@ -662,7 +662,9 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_c0[jb - 2], 0));
             // the latest bulk update issued at a step <= jb-2 (a later one belongs to panels the prologue
             // applies itself, waiting for it would serialise the chain behind the bulk work)
-            const int rd = (last_r <= jb - 2) ? last_r : prev_r;
+            // (pair region, odd step: the pair's own bulk update (step jb-2) does not touch this step's diagonal
+            // tile — the odd step's column update C1 did — so the one before it is the one to wait for)
+            const int rd = (pair_prev && (jb & 1) && last_r == jb - 2) ? prev_r : ((last_r <= jb - 2) ? last_r : prev_r);
             if (rd >= 0) CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_r[rd], 0));
         }
         const double *Tprev = jb > 0 ? A + j + (long long)(j - NB) * lda : nullptr;
@@ -739,10 +741,21 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             c.trace = w.trace ? w.trace + 8 * jb + 4 : nullptr;
             CVXB_TRY(dmma_gemm(c, T));
         }
+        // ---- T (odd step of a pair): block column jb+2 INCLUDING its diagonal tile gets both panels now, so that
+        // the diagonal chain two steps ahead does not wait for this pair's bulk update
+        if (odd && m > NB) {
+            GemmDesc c1;
+            c1.M = m; c1.N = m; c1.K = NB + wj;
+            c1.X = Wo; c1.Y = Wo; c1.ldx = ldw; c1.x_kmajor = false; c1.ldy = ldw; c1.y_kmajor = false;
+            c1.D = A22; c1.ldd = lda; c1.C = A22; c1.ldc = lda;
+            c1.alpha = -1.0; c1.beta = 1.0; c1.lower_only = true;
+            c1.ct_begin = panel_tiles; c1.ct_end = 2 * panel_tiles;
+            CVXB_TRY(dmma_gemm(c1, T));
+        }
         CVXB_CUDA(cudaEventRecord(w.ev_c0[jb], T));
         CVXB_TRY(copy_back_prev());
         // ---- U: the rest of the trailing matrix ----
-        if (m > NB && (!pair || odd)) {
+        if ((pair ? (odd && m > 2 * NB) : (m > NB))) {
             CVXB_CUDA(cudaStreamWaitEvent(U, w.ev_tr[jb], 0));
             GemmDesc u;
             u.M = m; u.N = m;
@@ -752,7 +765,7 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             u.ldy = ldw; u.y_kmajor = false;
             u.D = A22; u.ldd = lda; u.C = A22; u.ldc = lda;
             u.alpha = -1.0; u.beta = 1.0; u.lower_only = true;
-            u.ct_begin = panel_tiles; u.ct_end = 1 << 30;
+            u.ct_begin = odd ? 2 * panel_tiles : panel_tiles; u.ct_end = 1 << 30;
             u.trace = w.trace ? w.trace + 8 * jb + 6 : nullptr;
             CVXB_TRY(dmma_gemm(u, U));
             CVXB_CUDA(cudaEventRecord(w.ev_r[jb], U));
