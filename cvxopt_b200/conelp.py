@@ -32,7 +32,6 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
     import torch
     o = dict(DEFAULTS)
     o.update(options)
-    MAXITERS, ABSTOL, RELTOL, FEASTOL = int(o["maxiters"]), float(o["abstol"]), float(o["reltol"]), float(o["feastol"])
     lib = _lib.load()
     Gm = np.asarray(G, dtype=np.float64)
     if Gm.ndim != 2:
@@ -126,9 +125,6 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
         chk(lib.cvxb_sdot(xx.data_ptr(), yy.data_ptr(), C.byref(cd), C.byref(out), _lib.DEVICE), "sdot")
         return out.value
 
-    def snrm2(xx):
-        return math.sqrt(sdot(xx, xx))
-
     def max_step(xx, sigma=None):
         sync()
         out = C.c_double()
@@ -155,6 +151,49 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
                                 _lib.DEVICE), "G")
         if trans == "T" and sd and alpha:
             chk(lib.cvxb_triusc(xx.data_ptr(), C.byref(cd), _lib.DEVICE), "triusc")
+
+    def compute_scaling(ss, zz, lm):
+        sync()
+        chk(lib.cvxb_compute_scaling(ss.data_ptr(), zz.data_ptr(), lm.data_ptr(), C.byref(cd), C.byref(Wsc),
+                                     _lib.DEVICE), "compute_scaling")
+
+    def update_scaling(lm, dss, dzz):
+        sync()
+        chk(lib.cvxb_update_scaling(C.byref(Wsc), lm.data_ptr(), dss.data_ptr(), dzz.data_ptr(), C.byref(cd),
+                                    _lib.DEVICE), "update_scaling")
+
+    ops = (set_identity_scaling, factor, f3, scale, scale2, sprod, sinv, sdot, max_step, symm_blocks, Gf, compute_scaling,
+           update_scaling)
+    try:
+        return _conelp_core(torch, dev, cv, hv, n, dims, ops, o)
+    finally:
+        kkt.close()
+
+
+def _conelp_core(torch, dev, cv, hv, n, dims, ops, o):
+    """The driver itself: coneprog.conelp (coneprog.py:586-1436) on tensors that live on `dev`, every cone / KKT
+    operation through the 13 closures in `ops`.  `conelp` passes closures that call the B200 library with DEVICE
+    pointers; tests/test_conelp_twin_cpu.py passes closures made of the reference's own functions (CPU tensors) to
+    check this restatement of the driver logic where no GPU is available."""
+    (set_identity_scaling, factor, f3, scale, scale2, sprod, sinv, sdot, max_step, symm_blocks, Gf, compute_scaling,
+     update_scaling) = ops
+    MAXITERS, ABSTOL, RELTOL, FEASTOL = int(o["maxiters"]), float(o["abstol"]), float(o["reltol"]), float(o["feastol"])
+    show_progress = bool(o.get("show_progress", False))
+    debug_hook = o.get("debug_hook")
+    f64 = torch.float64
+    ml, q, sd = dims["l"], dims["q"], dims["s"]
+    cdim = ml + sum(q) + sum(k * k for k in sd)
+    cdim_diag = ml + sum(q) + sum(sd)
+    nlq = ml + sum(q)
+
+    def snrm2(xx):
+        return math.sqrt(sdot(xx, xx))
+
+    def zeros(k):
+        return torch.zeros(k, dtype=f64, device=dev)
+
+    def xdot(a, b):
+        return float(torch.dot(a, b))
 
     # index helpers for the 'q' cones: first entries, and the cone each 'q' row belongs to
     qfirst = torch.tensor(np.cumsum([0] + q[:-1], dtype=np.int64) + ml, dtype=torch.int64, device=dev) if q else None
@@ -189,12 +228,10 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
             o2 += m * m
             o3 += m
 
-    def zeros(k):
-        return torch.zeros(k, dtype=f64, device=dev)
 
     ct = torch.from_numpy(cv).to(dev)
     ht = torch.from_numpy(hv).to(dev)
-    resx0 = max(1.0, math.sqrt(float(torch.dot(ct, ct))))
+    resx0 = max(1.0, math.sqrt(xdot(ct, ct)))
     resz0 = max(1.0, snrm2(ht))
     resy0 = 1.0
 
@@ -223,7 +260,7 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
         tz = max_step(z)
         nrms, nrmz = snrm2(s), snrm2(z)
         gap = sdot(s, z)
-        pcost = float(torch.dot(ct, x))
+        pcost = xdot(ct, x)
         dcost = -sdot(ht, z)
         if pcost < 0.0:
             relgap = gap / -pcost
@@ -245,14 +282,14 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
             symm_blocks(s); symm_blocks(z)
             rxv = ct.clone()
             Gf(z, rxv, beta=1.0, trans="T")
-            resx = math.sqrt(float(torch.dot(rxv, rxv)))
+            resx = math.sqrt(xdot(rxv, rxv))
             rzv = zeros(cdim)
             Gf(x, rzv)
             rzv += s
             rzv -= ht
             resz = snrm2(rzv)
             return result("optimal", 0, fields={
-                "gap": gap, "relative gap": relgap, "primal objective": float(torch.dot(ct, x)),
+                "gap": gap, "relative gap": relgap, "primal objective": xdot(ct, x),
                 "dual objective": -sdot(ht, z), "primal infeasibility": resz / resz0, "primal slack": -ts,
                 "dual slack": -tz, "dual infeasibility": resx / resx0,
                 "residual as primal infeasibility certificate": None,
@@ -276,9 +313,9 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
         for iters in range(MAXITERS + 1):
             # hrx = -G'z ; rx = hrx - c*tau          (:861-870)
             Gf(z, hrx, alpha=-1.0, beta=0.0, trans="T")
-            hresx = math.sqrt(float(torch.dot(hrx, hrx)))
+            hresx = math.sqrt(xdot(hrx, hrx))
             rx.copy_(hrx).add_(ct, alpha=-tau)
-            resx = math.sqrt(float(torch.dot(rx, rx))) / tau
+            resx = math.sqrt(xdot(rx, rx)) / tau
             hresy, resy = 0.0, 0.0
             # hrz = s + G x ; rz = hrz - h*tau       (:883-893)
             Gf(x, hrz)
@@ -286,7 +323,7 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
             hresz = snrm2(hrz)
             rz.copy_(hrz).add_(ht, alpha=-tau)
             resz = snrm2(rz) / tau
-            cx, by, hz = float(torch.dot(ct, x)), 0.0, sdot(ht, z)
+            cx, by, hz = xdot(ct, x), 0.0, sdot(ht, z)
             rt = kappa + cx + by + hz
             pcost, dcost = cx / tau, -(by + hz) / tau
             if pcost < 0.0:
@@ -299,6 +336,12 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
             dres = resx / resx0
             pinfres = hresx / resx0 / (-hz - by) if hz + by < 0.0 else None
             dinfres = max(hresy / resy0, hresz / resz0) / (-cx) if cx < 0.0 else None
+            if debug_hook is not None:
+                debug_hook(iters, x, s, z, tau, kappa, rx, rz)
+            if show_progress:                    # the reference's progress line (:926-932), more digits
+                if iters == 0:
+                    print("% 10s% 12s% 10s% 8s% 7s % 5s" % ("pcost", "dcost", "gap", "pres", "dres", "k/t"))
+                print("%2d: % 8.4e % 8.4e % 4.0e% 7.1e% 7.1e% 7.0e" % (iters, pcost, dcost, gap, pres, dres, kappa / tau))
 
             if (pres <= FEASTOL and dres <= FEASTOL and (gap <= ABSTOL or (relgap is not None and relgap <= RELTOL))) \
                     or iters == MAXITERS:
@@ -331,9 +374,7 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
                     "residual as dual infeasibility certificate": dinfres})
 
             if iters == 0:                       # (:1033-1044)
-                sync()
-                chk(lib.cvxb_compute_scaling(s.data_ptr(), z.data_ptr(), lmbda.data_ptr(), C.byref(cd), C.byref(Wsc),
-                                             _lib.DEVICE), "compute_scaling")
+                compute_scaling(s, z, lmbda)
                 dg = math.sqrt(kappa / tau)
                 dgi = math.sqrt(tau / kappa)
                 lmbda[-1] = math.sqrt(tau * kappa)
@@ -370,14 +411,14 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
                 f3(xx, zz)
                 kappa_ = -kappa_ / lmbdag
                 tau_ = tau_ + kappa_ / dgi
-                tau_ = dgi * (tau_ + float(torch.dot(ct, xx)) + sdot(th, zz)) / (1.0 + z1z1)
+                tau_ = dgi * (tau_ + xdot(ct, xx) + sdot(th, zz)) / (1.0 + z1z1)
                 xx.add_(x1, alpha=tau_)
                 zz.add_(z1, alpha=tau_)
                 ss.sub_(zz)
                 kappa_ -= tau_
                 return tau_, kappa_
 
-            mu = float(torch.dot(lmbda, lmbda)) / (1 + cdim_diag)
+            mu = xdot(lmbda, lmbda) / (1 + cdim_diag)
             sigma = 0.0
             step = 1.0
             tt = tk = 0.0
@@ -429,9 +470,7 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
                     dz[o2:o2 + m * m].view(m, m).mul_(torch.sqrt(sigz[o3:o3 + m]).unsqueeze(1))
                     o2 += m * m
                     o3 += m
-            sync()
-            chk(lib.cvxb_update_scaling(C.byref(Wsc), lmbda.data_ptr(), ds.data_ptr(), dz.data_ptr(), C.byref(cd),
-                                        _lib.DEVICE), "update_scaling")
+            update_scaling(lmbda, ds, dz)
             dg *= math.sqrt(1.0 - step * tk) / math.sqrt(1.0 - step * tt)      # (:1403-1405)
             dgi = 1.0 / dg
             lmbda[-1] = lmbdag * math.sqrt(1.0 - step * tt) * math.sqrt(1.0 - step * tk)
@@ -445,4 +484,4 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
             gap = (float(torch.linalg.vector_norm(lmbda[:-1])) / tau) ** 2
         raise RuntimeError("unreachable")
     finally:
-        kkt.close()
+        pass    # (the caller owns the KKT factory and closes it)

@@ -9,7 +9,7 @@
 //                          (equal to the reference's  r = Lz^-T U lambda^1/2,  rti = Lz U lambda^-1/2  because
 //                          Lz' Ls V = U lambda;  two GEMMs instead of a triangular solve), singular values sorted
 //                          descending as LAPACK's gesvd returns them (:398, :611).
-// The SVD replaces lapack.gesvd (src/C/lapack.c gesvd binding); blocks of order <= 64 run all sweeps inside one CTA
+// The SVD replaces lapack.gesvd (src/C/lapack.c gesvd binding); blocks of order <= 48 run all sweeps inside one CTA
 // (shared memory), larger ones one launch per round of disjoint column pairs.
 #include "cone.cuh"
 #include <cmath>
@@ -188,16 +188,12 @@ __global__ void __launch_bounds__(128) jacobi_round_kernel(int m, int m2, int r,
     if (threadIdx.x == 0) atomicAdd(nrot, 1);
 }
 
-// Small blocks (m <= 64): the whole SVD iteration of one block inside one CTA, B and V in shared memory.
-// blockIdx.x = block index; Ball/Vall: concatenated m_k x m_k blocks at offsets off[k].
-__global__ void __launch_bounds__(256) jacobi_small_kernel(const int *ms, const int *off, double *Ball, double *Vall,
-                                                            int maxsweeps) {
+// Small blocks (m <= 48): the whole SVD iteration of one block inside one CTA, B and V in shared memory
+// (2 m^2 doubles <= 36 KB), one warp per column pair.
+__global__ void __launch_bounds__(256) jacobi_small_kernel(int m, double *Bg, double *Vg, int maxsweeps) {
     extern __shared__ double jsm[];
-    const int m = ms[blockIdx.x];
-    if (m <= 0) return;
     double *B = jsm, *V = jsm + m * m;
     __shared__ int rot;
-    double *Bg = Ball + off[blockIdx.x], *Vg = Vall + off[blockIdx.x];
     for (int e = threadIdx.x; e < m * m; e += blockDim.x) { B[e] = Bg[e]; V[e] = (e % m == e / m) ? 1.0 : 0.0; }
     __syncthreads();
     const int m2 = (m + 1) & ~1, npairs = m2 / 2;
@@ -313,6 +309,14 @@ int svd_jacobi(int m, double *B, double *Vw, double *U, double *V, double *sig, 
                cudaStream_t st) {
     if (m <= 0) return 0;
     const int T = 256, nb = (m * m + T - 1) / T;
+    if (m <= 48) {
+        jacobi_small_kernel<<<1, 256, 2 * (size_t)m * m * sizeof(double), st>>>(m, B, Vw, 30);
+        count_launch();
+        svd_finish_kernel<<<1, 256, 0, st>>>(m, B, Vw, U, V, sig, norms, perm);
+        count_launch();
+        CVXB_LAUNCH_CHECK();
+        return 0;
+    }
     set_identity_kernel<<<nb, T, 0, st>>>(m, Vw);
     count_launch();
     const int m2 = (m + 1) & ~1;
