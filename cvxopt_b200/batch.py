@@ -349,6 +349,9 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
                     it = torch.from_numpy(ix).to(dev)
                     sl = [t.index_select(0, it) for t in shard] if b.nsub > 1 else shard
                     keepalive.append(sl)
+                    # the library copies on the sub-batch's own stream: the slices (written on torch's current
+                    # stream) must be complete before it reads them
+                    torch.cuda.current_stream().synchronize()
                     part.load_ptr(sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(), sl[3].data_ptr(), _lib.DEVICE)
                 b.load_ptr_sliced(loader)
                 del keepalive
@@ -362,6 +365,7 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
                     status = np.zeros(kk, dtype=np.int32); iters = np.zeros(kk, dtype=np.int32)
                     pobj, dobj = np.zeros(kk), np.zeros(kk)
                     lib = part._lib
+                    torch.cuda.current_stream().synchronize()     # px/ps/pz may reuse blocks with work still queued
                     _lib.check(lib.cvxb_batch_results(part._h, px.data_ptr(), ps.data_ptr(), pz.data_ptr(), None, None,
                                                       None, None, _lib.DEVICE), "batch_results")
                     _lib.check(lib.cvxb_batch_results(part._h, None, None, None, status.ctypes.data, iters.ctypes.data,

@@ -164,8 +164,33 @@ def conelp(c, G, h, dims=None, kktsolver="chol", device=0, **options):
 
     ops = (set_identity_scaling, factor, f3, scale, scale2, sprod, sinv, sdot, max_step, symm_blocks, Gf, compute_scaling,
            update_scaling)
+    prof = o.get("profile")
+    if isinstance(prof, dict):
+        # options['profile'] = {}: wall time (device-synchronised) and call count per operation, 'total' for the solve
+        import time
+
+        def timed(name, f):
+            def g(*a, **k):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                try:
+                    return f(*a, **k)
+                finally:
+                    torch.cuda.synchronize(dev)
+                    e = prof.setdefault(name, [0.0, 0])
+                    e[0] += time.perf_counter() - t0
+                    e[1] += 1
+            return g
+        names = ("set_identity_scaling", "factor", "f3", "scale", "scale2", "sprod", "sinv", "sdot", "max_step",
+                 "symm_blocks", "Gf", "compute_scaling", "update_scaling")
+        ops = tuple(timed(nm, f) for nm, f in zip(names, ops))
+        t_all = time.perf_counter()
     try:
-        return _conelp_core(torch, dev, cv, hv, n, dims, ops, o)
+        sol = _conelp_core(torch, dev, cv, hv, n, dims, ops, o)
+        if isinstance(prof, dict):
+            torch.cuda.synchronize(dev)
+            prof["total"] = [time.perf_counter() - t_all, 1]
+        return sol
     finally:
         kkt.close()
 

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -38,7 +39,8 @@ constexpr int OZ_RING = 54;                // 4 KB units in the shared-memory ri
 constexpr int OZ_MAXST = 8;                // most stages a pass may split the ring into
 constexpr int OZ_MAXPASS = 5;
 constexpr int OZ_SMEM = OZ_RING * OZ_UNIT + 1024 + 256;
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 192;            // two-SM kernels: producer, issuer, 4 epilogue warps
+constexpr int OZ_THREADS1 = 320;           // one-SM kernel: producer, issuer, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int OZ_KRANGE = 32768 / OZ_KS;  // k steps per drain (int32 overflow bound)
 
 // byte offset of (row r of the unit = column of A, k byte kb) inside a 4 KB unit
@@ -65,6 +67,9 @@ struct OzParams {
     // and writes its 128 x 128 partial (tile-local, column-major) to part + b * 128*128; oz_tail_reduce_kernel sums them
     int nchunk, kper;
     double *part;
+    int kb2, kb5;              // k steps per ring stage for passes with <= 2 / <= 5 slices (CVXB_OZ_KB=a,b)
+    int trace_cta;             // diagnostics: CTA whose pass timeline goes to dbg (or -1)
+    int ablate;                // diagnostics (CVXB_OZ_ABLATE): 1 = no operand copies, 2 = no MMAs (results are then garbage)
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -128,6 +133,14 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// pass timeline of one CTA (CVXB_OZ_TRACE_CTA=<launch index>): globaltimer ns (low 32 bits) in dbg[16 + slot]
+__device__ __forceinline__ void dbg_stamp(const OzParams &p, int slot) {
+    if (p.dbg && p.trace_cta >= 0 && (int)blockIdx.x == p.trace_cta && slot < 48) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        *reinterpret_cast<volatile unsigned int *>(p.dbg + 16 + slot) = (unsigned int)t;
+    }
+}
 __device__ __forceinline__ void dbg_put(const OzParams &p, int slot, unsigned int v) {
     if (p.dbg && blockIdx.x == 0) {
         *reinterpret_cast<volatile unsigned int *>(p.dbg + slot) = v;
@@ -148,6 +161,11 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((OZ_T / 8) <
 // reads 8 KB per 64 cycles = the full 128 B/cycle of the SM, so the bulk copies that refill the ring compete
 // with it (the one-slice-pair kernel was 64 % busy, profiles/r01k); a 128x256x32 MMA reads 12 KB per 128 cycles.
 constexpr uint32_t OZ_IDESC_N256 = (2u << 4) | (1u << 7) | (1u << 10) | ((2 * OZ_T / 8) << 17) | ((OZ_T / 16) << 24);
+
+// k steps per ring stage: the producer / issuer handshake (barrier wait, commit, barrier wait) costs ~500 cycles per
+// stage (measured with copies and MMAs disabled, profiles/r02p), more than the 192 cycles of tensor work one k step
+// of pass {0,1} holds, so the passes with few slices put several k steps behind one handshake
+__device__ __forceinline__ int oz_kb(const OzParams &p, int nS) { return nS <= 2 ? p.kb2 : (nS <= 5 ? p.kb5 : 1); }
 
 template <int D0, int D1, bool FIRST>
 __device__ __forceinline__ void oz_issue_step(uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t tmem_base) {
@@ -172,7 +190,7 @@ __device__ __forceinline__ void oz_issue_step(uint32_t a_lo, uint32_t b_lo, uint
     }
 }
 
-__global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
+__global__ void __launch_bounds__(OZ_THREADS1, 1) oz_mma_kernel(OzParams p) {
     extern __shared__ uint8_t oz_smem_raw[];
     __shared__ uint32_t tmem_base_sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -191,7 +209,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
     if (tid == 0) {
         for (int s = 0; s < OZ_MAXST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
+        mbar_init(acc_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -204,6 +222,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
     dbg_put(p, 0, 0x100u + (tid == 0));
+    if (tid == 0) dbg_stamp(p, 0);
 
     const int S = p.S;
     const int npass = p.npass;
@@ -219,19 +238,24 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
                 const int k0 = kb + rg * OZ_KRANGE, k1 = min(ke, k0 + OZ_KRANGE);
                 for (int ps = 0; ps < npass; ++ps) {
                     const int nS = min(S, p.pd1[ps] + 1);
-                    const int nst = min(OZ_MAXST, OZ_RING / (2 * nS));
+                    const int KB = oz_kb(p, nS);
+                    const int nst = min(OZ_MAXST, OZ_RING / (2 * nS * KB));
                     const uint32_t bytes = (uint32_t)nS * OZ_UNIT;
                     // the new geometry overlaps the old stages: wait until every one of them is released
                     for (int s2 = 0; s2 < OZ_MAXST; ++s2)
                         if ((filled >> s2) & 1u) mbar_wait(empty + s2, (epar >> s2) & 1u);
                     int st = 0;
-                    for (int kc = k0; kc < k1; ++kc) {
+                    for (int kc = k0; kc < k1; kc += KB) {
+                        const int kn = min(KB, k1 - kc);
                         if ((filled >> st) & 1u) { mbar_wait(empty + st, (epar >> st) & 1u); epar ^= 1u << st; }
                         else filled |= 1u << st;
-                        mbar_expect_tx(full + st, 2 * bytes);
-                        uint8_t *sa = smem + (size_t)st * 2 * bytes;
-                        bulk_g2s(sa, p.Q + ((size_t)I * p.nk + kc) * (size_t)S * OZ_UNIT, bytes, full + st);
-                        bulk_g2s(sa + bytes, p.Q + ((size_t)J * p.nk + kc) * (size_t)S * OZ_UNIT, bytes, full + st);
+                        if (p.ablate & 1) { mbar_arrive(full + st); if (++st == nst) st = 0; continue; }
+                        mbar_expect_tx(full + st, 2 * bytes * (uint32_t)kn);
+                        uint8_t *sa = smem + (size_t)st * 2 * bytes * KB;
+                        for (int i = 0; i < kn; ++i, sa += 2 * bytes) {
+                            bulk_g2s(sa, p.Q + ((size_t)I * p.nk + kc + i) * (size_t)S * OZ_UNIT, bytes, full + st);
+                            bulk_g2s(sa + bytes, p.Q + ((size_t)J * p.nk + kc + i) * (size_t)S * OZ_UNIT, bytes, full + st);
+                        }
                         if (++st == nst) st = 0;
                     }
                 }
@@ -253,55 +277,65 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
             for (int ps = 0; ps < npass; ++ps, ++g) {
                 const int d0 = p.pd0[ps], d1 = p.pd1[ps];
                 const int nS = min(S, d1 + 1);
-                const int nst = min(OZ_MAXST, OZ_RING / (2 * nS));
+                const int KB = oz_kb(p, nS);
+                const int nst = min(OZ_MAXST, OZ_RING / (2 * nS * KB));
                 const uint32_t bytes = (uint32_t)nS * OZ_UNIT;
                 const int code = (p.layout == 0 && nS == d1 + 1) ? d0 * 16 + d1 : -1;
                 if (g > 0) { mbar_wait(acc_empty, (uint32_t)(g - 1) & 1); tc_fence_after(); }
+                if (lane == 0) dbg_stamp(p, 1 + 4 * g);
                 uint32_t touched = 0;
                 int st = 0;
-                for (int kc = k0; kc < k1; ++kc) {
+                for (int kc = k0; kc < k1; kc += KB) {
+                    const int kn = min(KB, k1 - kc);
                     mbar_wait(full + st, (cpar >> st) & 1u);
                     cpar ^= 1u << st;
                     tc_fence_after();
-                    const uint32_t a0 = sbase + (uint32_t)st * 2u * bytes;
-                    const uint32_t b0 = a0 + bytes;
-                    const bool firstk = (kc == k0);
                     if (elect_one()) {
+                        for (int i = 0; i < kn; ++i) {
+                            const uint32_t a0 = sbase + ((uint32_t)st * KB + (uint32_t)i) * 2u * bytes;
+                            const uint32_t b0 = a0 + bytes;
+                            const bool firstk = (kc + i == k0);
 #define OZ_CASE(D0, D1)                                                                              \
     case (D0) * 16 + (D1):                                                                           \
         if (firstk) oz_issue_step<D0, D1, true>(a0 >> 4, b0 >> 4, hi, tmem_base);                    \
         else oz_issue_step<D0, D1, false>(a0 >> 4, b0 >> 4, hi, tmem_base);                          \
         break;
-                        switch (code) {
-                            OZ_CASE(0, 0) OZ_CASE(1, 4) OZ_CASE(5, 8)          // S = 9: {0} {1..4} {5..8}
-                            OZ_CASE(0, 1) OZ_CASE(2, 4)                         // S = 9: {0,1} {2..4} {5..8}
-                            OZ_CASE(0, 3) OZ_CASE(4, 7)                         // S = 8: {0..3} {4..7}
-                            OZ_CASE(2, 5) OZ_CASE(6, 8) OZ_CASE(8, 8)
-                        default:
-                            for (int s = 0; s < nS; ++s) {
-                                const int tlo = max(0, d0 - s), thi = min(nS - 1, d1 - s);
-                                const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
-                                for (int tt = tlo; tt <= thi; ++tt) {
-                                    const int lev = s + tt - d0;
-                                    const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)((((b0 + tt * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
-                                    tc_mma_i8(tmem_base + lev * OZ_T, da, db, OZ_IDESC, (touched >> lev) & 1u);
-                                    touched |= 1u << lev;
+                            switch ((p.ablate & 2) ? -2 : code) {
+                                case -2: break;
+                                OZ_CASE(0, 0) OZ_CASE(1, 4) OZ_CASE(5, 8)          // S = 9: {0} {1..4} {5..8}
+                                OZ_CASE(0, 1) OZ_CASE(2, 4)                         // S = 9: {0,1} {2..4} {5..8}
+                                OZ_CASE(0, 3) OZ_CASE(4, 7)                         // S = 8: {0..3} {4..7}
+                                OZ_CASE(2, 5) OZ_CASE(6, 8) OZ_CASE(8, 8)
+                            default:
+                                for (int s = 0; s < nS; ++s) {
+                                    const int tlo = max(0, d0 - s), thi = min(nS - 1, d1 - s);
+                                    const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)((((a0 + s * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
+                                    for (int tt = tlo; tt <= thi; ++tt) {
+                                        const int lev = s + tt - d0;
+                                        const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)((((b0 + tt * OZ_UNIT) >> 4) & 0x3FFFu) | (lbo16 << 16));
+                                        tc_mma_i8(tmem_base + lev * OZ_T, da, db, OZ_IDESC, (touched >> lev) & 1u);
+                                        touched |= 1u << lev;
+                                    }
                                 }
                             }
-                        }
 #undef OZ_CASE
+                        }
                         tc_commit(empty + st);           // frees the stage when these MMAs have read it
                     }
                     __syncwarp();
                     if (++st == nst) st = 0;
                 }
+                if (lane == 0) dbg_stamp(p, 2 + 4 * g);
                 if (elect_one()) { tc_commit(acc_full); dbg_put(p, 2, 0x300u + g); }
                 __syncwarp();
             }
         }
     } else {
-        // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (rows of the tile) =====
+        // ===== epilogue: 8 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (rows of the tile) and one half of the
+        // columns: the values C already holds come from HBM / L2 under the full load of the operand stream (2-8 us per
+        // round trip, profiles/r02r), so the epilogue is bound by how many of those loads are in flight =====
         const int quad = warp & 3;
+        const int cbeg = ((warp - 2) >> 2) * (OZ_T / 2), cend = cbeg + OZ_T / 2;
         const int row = I * OZ_T + quad * 32 + lane;
         const bool row_ok = row < p.n;
         const double rsc = row_ok ? p.cs[row] : 0.0;
@@ -309,18 +343,39 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
         for (int rg = 0; rg < nrange; ++rg) {
             for (int ps = 0; ps < npass; ++ps, ++g) {
                 const int d0 = p.pd0[ps], nlev = p.pd1[ps] - d0 + 1;
-                mbar_wait(acc_full, (uint32_t)g & 1);
-                tc_fence_after();
                 // 2^(-12 - 7*(d0 + nlev - 1)): scale of the last level of the pass
                 const double lsc = ldexp(1.0, -12 - 7 * (d0 + nlev - 1));
                 const bool first = (g == 0);
-                for (int c0 = 0; c0 < OZ_T; c0 += 16) {
+                // The pass adds to what earlier passes left in C (or in the split-K partial tile): those values are
+                // loaded 16 columns ahead, as one batch of independent loads issued before the TMEM loads are waited
+                // for -- a load / add / store chain per column costs a global-memory latency per column.
+                double *const part0 = split ? p.part + (size_t)blockIdx.x * (OZ_T * OZ_T) + (quad * 32 + lane) : nullptr;
+                auto load_old = [&](int c0, double (&o)[16]) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int col = J * OZ_T + c0 + c;
+                        double v = 0.0;
+                        if (split) { if (!first) v = part0[(size_t)(c0 + c) * OZ_T]; }
+                        else if (row_ok && col < p.n && col <= row) {
+                            if (!first) v = p.C[row + (size_t)col * p.ldc];
+                            else if (p.D) v = p.beta * p.D[row + (size_t)col * p.ldd];
+                        }
+                        o[c] = v;
+                    }
+                };
+                double oldv[16], nxtv[16];
+                load_old(cbeg, oldv);                    // in flight while the pass's last MMAs run
+                mbar_wait(acc_full, (uint32_t)g & 1);
+                tc_fence_after();
+                if (warp == 4 && lane == 0) dbg_stamp(p, 3 + 4 * g);
+                for (int c0 = cbeg; c0 < cend; c0 += 16) {
                     uint32_t r[4][16];
                     const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
                     tc_ld16(ta, r[0]);
                     if (nlev > 1) tc_ld16(ta + OZ_T, r[1]);
                     if (nlev > 2) tc_ld16(ta + 2 * OZ_T, r[2]);
                     if (nlev > 3) tc_ld16(ta + 3 * OZ_T, r[3]);
+                    if (c0 + 16 < cend) load_old(c0 + 16, nxtv);
                     tc_wait_ld();
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
@@ -331,20 +386,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma_kernel(OzParams p) {
                         if (nlev > 3) v = fma(v, 128.0, (double)(int)r[3][c]);
                         if (split) {
                             v = (col < p.n) ? (v * lsc) * rsc * p.cs[col] : 0.0;
-                            double *dst = p.part + (size_t)blockIdx.x * (OZ_T * OZ_T) + (quad * 32 + lane) + (size_t)(c0 + c) * OZ_T;
-                            if (!first) v += *dst;
-                            *dst = v;
+                            part0[(size_t)(c0 + c) * OZ_T] = v + oldv[c];
                         } else if (row_ok && col < p.n && col <= row) {
                             v = (v * lsc) * rsc * p.cs[col];
-                            double *dst = p.C + row + (size_t)col * p.ldc;
-                            if (first) v += (p.D ? p.beta * p.D[row + (size_t)col * p.ldd] : 0.0);
-                            else v += *dst;
-                            *dst = v;
+                            p.C[row + (size_t)col * p.ldc] = v + oldv[c];
                         }
                     }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) oldv[c] = nxtv[c];
                 }
                 tc_fence_before();
                 __syncwarp();
+                if (warp == 4 && lane == 0) dbg_stamp(p, 4 + 4 * g);
                 if (lane == 0) mbar_arrive(acc_empty);
                 if (quad == 0 && lane == 0) dbg_put(p, 3, 0x400u + g);
             }
@@ -419,24 +472,38 @@ __device__ __forceinline__ uint32_t cluster_rank() {
     return r;
 }
 
-// one k step of a pass (levels D0..D1): A slices are 4 KB units, B slices 2 KB half units
-template <int D0, int D1, bool FIRST>
+// WIDE form (N = 256): the pair computes the 256 x 256 block of row blocks {2a, 2a+1} x column blocks {2b, 2b+1};
+// each CTA stages its 128 rows of the M operand and ITS 128 rows of the N operand (block 2b + rank, whole 4 KB
+// units), the MMA is 256x256x32 (idesc N = 256) and an accumulator level takes 256 TMEM columns, so a pass
+// holds two levels.  Per 128x128 of output a CTA ingests 25 x 4 KB per k step (passes {0} {1,2} {3,4} {5,6} {7,8})
+// where the one-SM kernel ingests 32 x 4 KB (passes {0,1} {2..4} {5..8}).
+constexpr uint32_t OZ_IDESC2W = (2u << 4) | (1u << 7) | (1u << 10) | ((2 * OZ_T / 8) << 17) | ((2 * OZ_T / 16) << 24);
+
+// one k step of a pass (levels D0..D1): A slices are 4 KB units, B slices 2 KB half units (4 KB units if WIDE)
+template <int D0, int D1, bool FIRST, bool WIDE>
 __device__ __forceinline__ void oz_issue_step2(uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t tmem_base) {
     constexpr int NS = D1 + 1;
+    constexpr int BU = WIDE ? OZ_UNIT : OZ_HALF;
+    constexpr int LW = WIDE ? 2 * OZ_T : OZ_T;
+    constexpr uint32_t ID = WIDE ? OZ_IDESC2W : OZ_IDESC2;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(a_lo + s * (OZ_UNIT >> 4));
 #pragma unroll
         for (int tt = 0; tt < NS; ++tt) {
             if (s + tt >= D0 && s + tt <= D1) {
-                const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(b_lo + tt * (OZ_HALF >> 4));
-                tc_mma2_i8(tmem_base + (s + tt - D0) * OZ_T, da, db, OZ_IDESC2, (FIRST && s == 0) ? 0u : 1u);
+                const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(b_lo + tt * (BU >> 4));
+                tc_mma2_i8(tmem_base + (s + tt - D0) * LW, da, db, ID, (FIRST && s == 0) ? 0u : 1u);
             }
         }
     }
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
+    constexpr int BU = WIDE ? OZ_UNIT : OZ_HALF;          // bytes of one staged B slice
+    constexpr int LW = WIDE ? 2 * OZ_T : OZ_T;            // TMEM columns of one accumulator level
+    constexpr uint32_t ID = WIDE ? OZ_IDESC2W : OZ_IDESC2;
     extern __shared__ uint8_t oz_smem_raw[];
     __shared__ uint32_t tmem_base_sh;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -447,12 +514,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
     uint64_t *full = bars, *empty = bars + OZ_MAXST, *pfull = bars + 2 * OZ_MAXST, *acc_full = bars + 3 * OZ_MAXST,
              *acc_empty = bars + 3 * OZ_MAXST + 1;
 
-    // pair (a, J): row blocks 2a (leader) and 2a + 1 (peer), column block J
+    // pair (a, J): row blocks 2a (leader) and 2a + 1 (peer), column block J  (WIDE: column blocks 2J, 2J + 1)
     const unsigned int tl = p.tiles[blockIdx.x >> 1];
     const int a = (int)(tl >> 16), J = (int)(tl & 0xFFFFu);
     int I = 2 * a + (int)rank;
     const bool live = I < p.nblk;                // odd nblk: the last pair has no second row block
     if (!live) I = 2 * a;                        // load valid data, store nothing
+    const int Jb = WIDE ? min(2 * J + (int)rank, p.nblk - 1) : J;     // block whose rows this CTA stages for N
+    const int Jc = WIDE ? 2 * J : J;                                  // first column block of the accumulators
 
     if (tid == 0) {
         for (int s = 0; s < OZ_MAXST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(pfull + s, 1); }
@@ -484,7 +553,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
                 const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
                 for (int ps = 0; ps < npass; ++ps) {
                     const int nS = min(S, p.pd1[ps] + 1);
-                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + OZ_HALF);
+                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + BU);
                     const int nst = min(OZ_MAXST, (OZ_RING * OZ_UNIT) / (int)sbytes);
                     for (int s2 = 0; s2 < OZ_MAXST; ++s2)
                         if ((filled >> s2) & 1u) mbar_wait(empty + s2, (epar >> s2) & 1u);
@@ -492,12 +561,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
                     for (int kc = k0; kc < k1; ++kc) {
                         if ((filled >> st) & 1u) { mbar_wait(empty + st, (epar >> st) & 1u); epar ^= 1u << st; }
                         else filled |= 1u << st;
+                        if (p.ablate & 1) { mbar_arrive(full + st); if (++st == nst) st = 0; continue; }
                         mbar_expect_tx(full + st, sbytes);
                         uint8_t *sa = smem + (size_t)st * sbytes;
                         bulk_g2s(sa, p.Q + ((size_t)I * p.nk + kc) * (size_t)S * OZ_UNIT, (uint32_t)nS * OZ_UNIT, full + st);
-                        const uint8_t *qb = p.Q + ((size_t)J * p.nk + kc) * (size_t)S * OZ_UNIT + (size_t)rank * OZ_HALF;
                         uint8_t *sb = sa + (size_t)nS * OZ_UNIT;
-                        for (int s = 0; s < nS; ++s) bulk_g2s(sb + (size_t)s * OZ_HALF, qb + (size_t)s * OZ_UNIT, OZ_HALF, full + st);
+                        if (WIDE) {
+                            bulk_g2s(sb, p.Q + ((size_t)Jb * p.nk + kc) * (size_t)S * OZ_UNIT, (uint32_t)nS * OZ_UNIT, full + st);
+                        } else {
+                            const uint8_t *qb = p.Q + ((size_t)J * p.nk + kc) * (size_t)S * OZ_UNIT + (size_t)rank * OZ_HALF;
+                            for (int s = 0; s < nS; ++s) bulk_g2s(sb + (size_t)s * OZ_HALF, qb + (size_t)s * OZ_UNIT, OZ_HALF, full + st);
+                        }
                         if (++st == nst) st = 0;
                     }
                 }
@@ -514,7 +588,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
                 const int k0 = rg * OZ_KRANGE, k1 = min(p.nk, k0 + OZ_KRANGE);
                 for (int ps = 0; ps < npass; ++ps) {
                     const int nS = min(S, p.pd1[ps] + 1);
-                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + OZ_HALF);
+                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + BU);
                     const int nst = min(OZ_MAXST, (OZ_RING * OZ_UNIT) / (int)sbytes);
                     int st = 0;
                     for (int kc = k0; kc < k1; ++kc) {
@@ -535,7 +609,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
                 for (int ps = 0; ps < npass; ++ps, ++g) {
                     const int d0 = p.pd0[ps], d1 = p.pd1[ps];
                     const int nS = min(S, d1 + 1);
-                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + OZ_HALF);
+                    const uint32_t sbytes = (uint32_t)nS * (OZ_UNIT + BU);
                     const int nst = min(OZ_MAXST, (OZ_RING * OZ_UNIT) / (int)sbytes);
                     const int code = (nS == d1 + 1) ? d0 * 16 + d1 : -1;
                     if (g > 0) { mbar_wait_cluster(acc_empty, (uint32_t)(g - 1) & 1); tc_fence_after(); }
@@ -552,22 +626,31 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
                         if (elect_one()) {
 #define OZ_CASE2(D0, D1)                                                                             \
     case (D0) * 16 + (D1):                                                                           \
-        if (firstk) oz_issue_step2<D0, D1, true>(a0 >> 4, b0 >> 4, hi, tmem_base);                   \
-        else oz_issue_step2<D0, D1, false>(a0 >> 4, b0 >> 4, hi, tmem_base);                         \
+        if (firstk) oz_issue_step2<D0, D1, true, WIDE>(a0 >> 4, b0 >> 4, hi, tmem_base);             \
+        else oz_issue_step2<D0, D1, false, WIDE>(a0 >> 4, b0 >> 4, hi, tmem_base);                   \
         break;
-                            switch (code) {
+                            switch ((p.ablate & 2) ? -2 : (WIDE ? code + 4096 : code)) {
+                                case -2: break;
                                 OZ_CASE2(0, 0) OZ_CASE2(1, 4) OZ_CASE2(5, 8)
                                 OZ_CASE2(0, 1) OZ_CASE2(2, 4)
                                 OZ_CASE2(0, 3) OZ_CASE2(4, 7)
                                 OZ_CASE2(2, 5) OZ_CASE2(6, 8) OZ_CASE2(8, 8)
+#define OZ_CASE2W(D0, D1)                                                                            \
+    case 4096 + (D0) * 16 + (D1):                                                                    \
+        if (firstk) oz_issue_step2<D0, D1, true, true>(a0 >> 4, b0 >> 4, hi, tmem_base);             \
+        else oz_issue_step2<D0, D1, false, true>(a0 >> 4, b0 >> 4, hi, tmem_base);                   \
+        break;
+                                OZ_CASE2W(0, 0) OZ_CASE2W(1, 2) OZ_CASE2W(3, 4) OZ_CASE2W(5, 6) OZ_CASE2W(7, 8)
+                                OZ_CASE2W(0, 1) OZ_CASE2W(2, 3) OZ_CASE2W(4, 5) OZ_CASE2W(6, 7)
+#undef OZ_CASE2W
                             default:
                                 for (int s = 0; s < nS; ++s) {
                                     const int tlo = max(0, d0 - s), thi = min(nS - 1, d1 - s);
                                     const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(((a0 + s * OZ_UNIT) >> 4) & 0x3FFFu);
                                     for (int tt = tlo; tt <= thi; ++tt) {
                                         const int lev = s + tt - d0;
-                                        const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(((b0 + tt * OZ_HALF) >> 4) & 0x3FFFu);
-                                        tc_mma2_i8(tmem_base + lev * OZ_T, da, db, OZ_IDESC2, (touched >> lev) & 1u);
+                                        const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(((b0 + tt * BU) >> 4) & 0x3FFFu);
+                                        tc_mma2_i8(tmem_base + lev * LW, da, db, ID, (touched >> lev) & 1u);
                                         touched |= 1u << lev;
                                     }
                                 }
@@ -598,29 +681,43 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_mma2_kernel(OzParams p) {
                 tc_fence_after();
                 const double lsc = ldexp(1.0, -12 - 7 * (d0 + nlev - 1));
                 const bool first = (g == 0);
-                for (int c0 = 0; c0 < OZ_T; c0 += 16) {
+                auto load_old = [&](int c0, double (&o)[16]) {          // see oz_mma_kernel
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int col = Jc * OZ_T + c0 + c;
+                        double v = 0.0;
+                        if (row_ok && col < p.n && col <= row) {
+                            if (!first) v = p.C[row + (size_t)col * p.ldc];
+                            else if (p.D) v = p.beta * p.D[row + (size_t)col * p.ldd];
+                        }
+                        o[c] = v;
+                    }
+                };
+                double oldv[16], nxtv[16];
+                load_old(0, oldv);
+                for (int c0 = 0; c0 < LW; c0 += 16) {
                     uint32_t r[4][16];
                     const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + c0;
                     tc_ld16(ta, r[0]);
-                    if (nlev > 1) tc_ld16(ta + OZ_T, r[1]);
-                    if (nlev > 2) tc_ld16(ta + 2 * OZ_T, r[2]);
-                    if (nlev > 3) tc_ld16(ta + 3 * OZ_T, r[3]);
+                    if (nlev > 1) tc_ld16(ta + LW, r[1]);
+                    if (!WIDE && nlev > 2) tc_ld16(ta + 2 * LW, r[2]);
+                    if (!WIDE && nlev > 3) tc_ld16(ta + 3 * LW, r[3]);
+                    if (c0 + 16 < LW) load_old(c0 + 16, nxtv);
                     tc_wait_ld();
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const int col = J * OZ_T + c0 + c;
+                        const int col = Jc * OZ_T + c0 + c;
                         double v = (double)(int)r[0][c];
                         if (nlev > 1) v = fma(v, 128.0, (double)(int)r[1][c]);
-                        if (nlev > 2) v = fma(v, 128.0, (double)(int)r[2][c]);
-                        if (nlev > 3) v = fma(v, 128.0, (double)(int)r[3][c]);
+                        if (!WIDE && nlev > 2) v = fma(v, 128.0, (double)(int)r[2][c]);
+                        if (!WIDE && nlev > 3) v = fma(v, 128.0, (double)(int)r[3][c]);
                         if (row_ok && col < p.n && col <= row) {
                             v = (v * lsc) * rsc * p.cs[col];
-                            double *dst = p.C + row + (size_t)col * p.ldc;
-                            if (first) v += (p.D ? p.beta * p.D[row + (size_t)col * p.ldd] : 0.0);
-                            else v += *dst;
-                            *dst = v;
+                            p.C[row + (size_t)col * p.ldc] = v + oldv[c];
                         }
                     }
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) oldv[c] = nxtv[c];
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -679,14 +776,28 @@ __global__ void oz_colscale_kernel(int m, int n, const double *A, long long lda,
     }
 }
 
-// digits of column block cb, k steps [kc0, kc0 + gridDim.x chunk): thread r = column cb*128 + r
+// digits of column block cb, k step kc (one 128-column x 32-row block of Gs = 9 units).  The block is read with
+// coalesced 256-byte rows (lane = k, one column per load instruction) into shared memory and sliced from there by one
+// thread per column; reading it with one thread per column straight from global memory (32 distinct lines per load
+// instruction) ran at 3 TB/s (742 us at n=8192, m=16384, profiles/r02n launch list).
 __global__ void __launch_bounds__(OZ_T) oz_slice_kernel(int m, int n, const double *A, long long lda, const double *d,
                                                         const double *sinv, uint8_t *Q, int nk, int S, int layout) {
-    const int cb = blockIdx.y, kc = blockIdx.x, r = threadIdx.x;
+    __shared__ double tile[OZ_T][OZ_KS + 1];
+    const int cb = blockIdx.y, kc = blockIdx.x, r = threadIdx.x, lane = r & 31, warp = r >> 5;
+    {
+        const int k = kc * OZ_KS + lane;
+        const double dk = (k < m) ? (d ? d[k] : 1.0) : 0.0;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {
+            const int cc = warp * 32 + c, j = cb * OZ_T + cc;
+            double x = 0.0;
+            if (j < n && k < m) x = dk * A[(size_t)j * lda + k];
+            tile[cc][lane] = x;
+        }
+    }
+    __syncthreads();
     const int j = cb * OZ_T + r;
-    const bool col_ok = j < n;
-    const double sc = col_ok ? sinv[j] : 0.0;
-    const double *a = A + (size_t)(col_ok ? j : 0) * lda;
+    const double sc = (j < n) ? sinv[j] : 0.0;
     uint8_t *unit0 = Q + ((size_t)cb * nk + kc) * (size_t)S * OZ_UNIT;
     for (int half = 0; half < 2; ++half) {
         uint32_t pk[OZ_SMAX][4];
@@ -694,9 +805,7 @@ __global__ void __launch_bounds__(OZ_T) oz_slice_kernel(int m, int n, const doub
         for (int s = 0; s < OZ_SMAX; ++s) pk[s][0] = pk[s][1] = pk[s][2] = pk[s][3] = 0u;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-            const int k = kc * OZ_KS + half * 16 + e;
-            double x = 0.0;
-            if (col_ok && k < m) x = ((d ? d[k] : 1.0) * a[k]) * sc;      // |x| < 64
+            double x = tile[r][half * 16 + e] * sc;                          // |x| < 64 (0 outside the matrix)
 #pragma unroll
             for (int s = 0; s < OZ_SMAX; ++s) {
                 if (s < S) {
@@ -778,7 +887,8 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     static DeviceOnce once;
     if (const unsigned long long bit = once.pending()) {
         CVXB_CUDA(cudaFuncSetAttribute(oz_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-        CVXB_CUDA(cudaFuncSetAttribute(oz_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        CVXB_CUDA(cudaFuncSetAttribute(oz_mma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        CVXB_CUDA(cudaFuncSetAttribute(oz_mma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
         once.mark(bit);
     }
     const int nblk = (n + OZ_T - 1) / OZ_T, nk = std::max(1, (m + OZ_KS - 1) / OZ_KS);
@@ -795,14 +905,42 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     // CVXB_OZ_2SM=1 selects the two-SM (cta_group::2) kernel.  Measured on B200 (profiles/r02c): correct, but a
     // 256x128x32 int8 MMA issued for the SM pair takes 128 cycles (the pair runs at the rate of ONE SM's
     // 128x128x32), so 21.5-24.8 ms against 18.5 ms for the one-SM kernel at n=8192, m=16384: off by default.
-    bool two_sm = false;
-    if (const char *e = getenv("CVXB_OZ_2SM")) two_sm = layout == 0 && e[0] == '1';
+    // CVXB_OZ_2SM=2 selects the WIDE two-SM kernel (256x256x32 MMAs, 256x256 blocks of C per SM pair).
+    int two_sm = 0;
+    if (const char *e = getenv("CVXB_OZ_2SM")) two_sm = (layout == 0 && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
     std::vector<unsigned int> order;
     order.reserve((size_t)tiles);
     int band = 12;
     if (const char *e = getenv("CVXB_OZ_BAND")) band = std::max(1, atoi(e));
-    long long npairs = 0;
-    if (two_sm) {
+    static int tail_on = -1;
+    if (tail_on < 0) { const char *e = getenv("CVXB_OZ_TAIL"); tail_on = (e && e[0] == '0') ? 0 : 1; }
+    const int npairs_hw = kNumSMs / 2;
+    long long npairs = 0, nmain2 = 0;
+    if (two_sm == 2) {
+        // 256 x 256 blocks (a, b), a >= b, band-major; the blocks of the last partial wave of SM pairs are handed to
+        // the one-SM kernel as 128 x 128 tiles split along K (below)
+        const int na = (nblk + 1) / 2, pband = std::max(1, band / 2);
+        for (int a0 = 0; a0 < na; a0 += pband) {
+            const int a1 = std::min(na, a0 + pband);
+            for (int b = 0; b < a1; ++b)
+                for (int a = std::max(a0, b); a < a1; ++a) order.push_back(((unsigned)a << 16) | (unsigned)b);
+        }
+        npairs = (long long)order.size();
+        nmain2 = npairs;
+        const long long rem = npairs % npairs_hw;
+        if (tail_on && npairs > npairs_hw && rem > 0 && 4 * rem <= kNumSMs / 2) nmain2 = npairs - rem;
+        std::vector<unsigned int> t128;
+        for (long long q = nmain2; q < npairs; ++q) {
+            const int a = (int)(order[(size_t)q] >> 16), b = (int)(order[(size_t)q] & 0xFFFFu);
+            for (int di = 0; di < 2; ++di)
+                for (int dj = 0; dj < 2; ++dj) {
+                    const int I = 2 * a + di, J = 2 * b + dj;
+                    if (I < nblk && J < nblk && I >= J) t128.push_back(((unsigned)I << 16) | (unsigned)J);
+                }
+        }
+        order.resize((size_t)nmain2);
+        order.insert(order.end(), t128.begin(), t128.end());
+    } else if (two_sm == 1) {
         // pairs of row blocks (2a, 2a+1) x column block J with 2a+1 >= J (the tile (2a, J) of a pair that
         // straddles the diagonal is computed and masked), same band-major launch order
         const int na = (nblk + 1) / 2, pband = std::max(1, band / 2);
@@ -812,7 +950,7 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
                 for (int a = std::max(a0, J / 2); a < a1; ++a)
                     if (2 * a + 1 >= J) order.push_back(((unsigned)a << 16) | (unsigned)J);
         }
-        npairs = (long long)order.size();
+        npairs = nmain2 = (long long)order.size();
     } else {
         for (int r0 = 0; r0 < nblk; r0 += band) {
             const int r1 = std::min(nblk, r0 + band);
@@ -820,6 +958,7 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
                 for (int I = std::max(r0, J); I < r1; ++I) order.push_back(((unsigned)I << 16) | (unsigned)J);
         }
     }
+    if ((long long)order.size() > tiles) { set_error("ozaki_syrk: tile list overflow"); return CVXB_E_ARG; }
     CVXB_CUDA(cudaMemcpyAsync(dtiles, order.data(), order.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
     oz_colscale_kernel<<<n, 256, 0, st>>>(m, n, A, lda, d, cs, sinv);
     count_launch();
@@ -828,10 +967,28 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     OzParams p;
     p.Q = Q; p.cs = cs; p.D = D; p.ldd = ldd; p.C = C; p.ldc = ldc; p.beta = beta;
     p.n = n; p.nblk = nblk; p.nk = nk; p.S = S; p.layout = layout; p.dbg = dbg; p.tiles = dtiles;
+    p.nchunk = 1; p.kper = nk; p.part = nullptr;
+    p.ablate = 0;
+    p.trace_cta = -1;
+    if (const char *e = getenv("CVXB_OZ_TRACE_CTA")) p.trace_cta = atoi(e);
+    p.kb2 = 4; p.kb5 = 1;
+    if (const char *e = getenv("CVXB_OZ_KB")) {
+        int a = 0, b = 0;
+        if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 6 && b >= 1 && b <= 2) { p.kb2 = a; p.kb5 = b; }
+    }
+    if (const char *e = getenv("CVXB_OZ_ABLATE")) p.ablate = atoi(e);
     oz_choose_groups(S, &p.npass, p.pd0, p.pd1);
+    long long t1_first = 0, t1_count = tiles;            // 128 x 128 tiles left to the one-SM kernel
     if (two_sm) {
+        OzParams p2 = p;
+        if (two_sm == 2) {                                // two levels per pass: {0} {1,2} {3,4} ... (S odd) / {0,1} {2,3} ...
+            int np = 0, dlev = 0;
+            if (S & 1) { p2.pd0[np] = 0; p2.pd1[np] = 0; ++np; dlev = 1; }
+            for (; dlev < S; dlev += 2, ++np) { p2.pd0[np] = dlev; p2.pd1[np] = dlev + 1; }
+            p2.npass = np;
+        }
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(2 * npairs), 1, 1);
+        cfg.gridDim = dim3((unsigned)(2 * nmain2), 1, 1);
         cfg.blockDim = dim3(OZ_THREADS, 1, 1);
         cfg.dynamicSmemBytes = OZ_SMEM;
         cfg.stream = st;
@@ -839,28 +996,33 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        CVXB_CUDA(cudaLaunchKernelEx(&cfg, oz_mma2_kernel, p));
-    } else {
+        if (nmain2 > 0) {
+            if (two_sm == 2) CVXB_CUDA(cudaLaunchKernelEx(&cfg, oz_mma2_kernel<true>, p2));
+            else CVXB_CUDA(cudaLaunchKernelEx(&cfg, oz_mma2_kernel<false>, p2));
+        }
+        t1_first = nmain2;
+        t1_count = (long long)order.size() - nmain2;
+    }
+    if (t1_count > 0) {
         // The last, partial wave of tiles (2080 = 14 x 148 + 8 at n = 8192) would leave most SMs idle for a whole
         // tile time: its tiles are split along K over all SMs (partials + ordered reduce).  CVXB_OZ_TAIL=0 disables.
-        p.nchunk = 1; p.kper = nk; p.part = nullptr;
-        long long tmain = tiles;
-        int ntail = (int)(tiles % kNumSMs), nchunk = 1;
-        static int tail_on = -1;
-        if (tail_on < 0) { const char *e = getenv("CVXB_OZ_TAIL"); tail_on = (e && e[0] == '0') ? 0 : 1; }
-        if (tail_on && tiles > kNumSMs && ntail > 0 && ntail <= kNumSMs / 2) {
+        long long tmain = t1_count;
+        int ntail = (int)(t1_count % kNumSMs), nchunk = 1;
+        if (tail_on && (two_sm || t1_count > kNumSMs) && ntail > 0 && ntail <= kNumSMs / 2) {
             nchunk = std::min(kNumSMs / ntail, nk);
-            if (nchunk >= 2) tmain = tiles - ntail; else nchunk = 1;
+            if (nchunk >= 2) tmain = t1_count - ntail; else nchunk = 1;
         }
-        if (tmain > 0) oz_mma_kernel<<<(unsigned)tmain, OZ_THREADS, OZ_SMEM, st>>>(p);
+        OzParams pm = p;
+        pm.tiles = dtiles + t1_first;
+        if (tmain > 0) { oz_mma_kernel<<<(unsigned)tmain, OZ_THREADS1, OZ_SMEM, st>>>(pm); if (two_sm) count_launch(); }
         if (nchunk >= 2) {
             OzParams pt = p;
-            pt.tiles = dtiles + tmain;
+            pt.tiles = dtiles + t1_first + tmain;
             pt.nchunk = nchunk;
             pt.kper = (nk + nchunk - 1) / nchunk;
             pt.nchunk = (nk + pt.kper - 1) / pt.kper;                 // no empty chunk
             pt.part = reinterpret_cast<double *>(((uintptr_t)(Q + (size_t)nblk * nk * S * OZ_UNIT) + 255) & ~uintptr_t(255));
-            oz_mma_kernel<<<(unsigned)(ntail * pt.nchunk), OZ_THREADS, OZ_SMEM, st>>>(pt);
+            oz_mma_kernel<<<(unsigned)(ntail * pt.nchunk), OZ_THREADS1, OZ_SMEM, st>>>(pt);
             oz_tail_reduce_kernel<<<dim3(OZ_T * OZ_T / 256, ntail), 256, 0, st>>>(pt, ntail);
             count_launch(2);
         }

@@ -78,3 +78,26 @@ def test_concurrent_subbatches_match_single_batch():
     assert all(s == "optimal" for s in three["status"])
     np.testing.assert_allclose(three["x"], one["x"], rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(three["primal objective"], one["primal objective"], rtol=1e-12)
+
+
+def test_distributed_entry_single_process_matches_qp_batch():
+    """qp_batch_distributed without a process group (the bench's N=1 leg): device-side slicing into concurrent
+    sub-batches must give exactly qp_batch's per-problem results.  Sized so that the slices are ~100 MB each: the
+    library's copies run on the sub-batches' own streams and once raced with the torch kernels that write the
+    slices (stale blocks of the caching allocator held OTHER problems' data: every solve still 'optimal', wrong
+    iteration counts)."""
+    import torch
+    import cvxopt_b200
+    B, n, m = 96, 192, 384
+    P, q, G, h = make_batch(B, n, m, seed0=300)
+    want = cvxopt_b200.qp_batch(P, q, G, h, nsub=2)
+    for rep in range(3):
+        # churn the caching allocator so that freed blocks hold unrelated problem data
+        junk = [torch.randn(B * m * n // 2, dtype=torch.float64, device="cuda") for _ in range(3)]
+        del junk
+        tm = {}
+        got = cvxopt_b200.qp_batch_distributed(P, q, G, h, nsub=2, timings=tm)["all"]
+        assert list(got["iterations"]) == list(want["iterations"])
+        np.testing.assert_allclose(got["x"], want["x"], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(got["primal objective"], want["primal objective"], rtol=1e-12)
+        assert set(tm) >= {"setup_ms", "scatter_ms", "solve_ms", "gather_ms"}

@@ -68,4 +68,6 @@ def test_device_conelp_on_configs_3_and_5(name, n, dims):
     # (tests/test_fullsize_gpu.py).
     assert abs(got["iterations"] - b["iterations"]) <= 1
     np.testing.assert_allclose(got["primal objective"], b["primal objective"], rtol=1e-8)
-    np.testing.assert_allclose(got["dual objective"], b["dual objective"], rtol=1e-7)
+    # the duality gap at termination is within reltol = 1e-6 of the objective; one iteration more or less moves the
+    # dual objective inside that gap
+    np.testing.assert_allclose(got["dual objective"], b["dual objective"], rtol=1e-6)

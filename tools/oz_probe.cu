@@ -53,8 +53,8 @@ int main(int argc, char **argv) {
     if (onehot) { n = 128; m = 32; S = 1; }
     if (ints) S = 1;
     CK(cudaSetDevice(0));
-    CK(cudaHostAlloc(&g_dbg, 64, cudaHostAllocMapped));
-    memset(g_dbg, 0, 64);
+    CK(cudaHostAlloc(&g_dbg, 512, cudaHostAllocMapped));
+    memset(g_dbg, 0, 512);
     unsigned int *ddbg = nullptr;
     CK(cudaHostGetDevicePointer(&ddbg, g_dbg, 0));
     cudaStream_t st; CK(cudaStreamCreate(&st));
@@ -93,6 +93,14 @@ int main(int argc, char **argv) {
     if (int w = wait_stream(st, 10.0)) return w;
     printf("launch finished; dbg:");
     for (int i = 0; i < 4; ++i) printf(" %x", g_dbg[i]);
+    if (getenv("CVXB_OZ_TRACE_CTA")) {
+        // pass timeline of the traced CTA (us after its start): issue start, issue end, accumulators complete, epilogue end
+        printf("\n  trace:");
+        for (int g = 0; g < 5 && g_dbg[16 + 1 + 4 * g]; ++g) {
+            printf("  pass %d:", g);
+            for (int q = 1; q <= 4; ++q) printf(" %.1f", (double)(g_dbg[16 + q + 4 * g] - g_dbg[16]) * 1e-3);
+        }
+    }
     printf("\n");
     std::vector<double> C((size_t)n * n);
     CK(cudaMemcpy(C.data(), dC, C.size() * 8, cudaMemcpyDeviceToHost));
