@@ -137,7 +137,7 @@ __global__ void k_res_dots(Ptrs p) {
 }
 // statistics + stopping rule (:2175-2234)
 __global__ void k_stats(Ptrs p, int iter, int maxiters, double abstol, double reltol, double feastol,
-                        int *ndone) {
+                        int *ndone, int *doneflags) {
     PB_SETUP
     double rx2 = 0, rz2 = 0, zrz = 0;
     for (int i = tid; i < p.n; i += nt) { double v = p.rx[on + i]; rx2 += v * v; }
@@ -161,8 +161,53 @@ __global__ void k_stats(Ptrs p, int iter, int maxiters, double abstol, double re
             }
         }
         if (S.done) atomicAdd(ndone, 1);
+        doneflags[b] = S.done;
     }
 }
+
+// ---- compaction of finished problems ----
+// The lock-step loop launches every batched kernel over the first `Bact` slots.  When problems finish, each finished
+// slot below the new active count trades places with an active slot from the tail: everything a problem owns between
+// iterations (P, G, its 17 vectors, its scalars; K / inv / info are rebuilt every iteration) is swapped, so the active
+// problems stay a contiguous prefix and finished ones keep their final iterates in the tail.  ~6.3 MB per swap at
+// n=512, m=1024, at most one swap per problem per solve.
+struct SwapArgs {
+    double *P, *G, *vecs; Scal *sc;
+    long long sP, sG;
+    int n, me, Btot;
+};
+__global__ void k_swap_slots(SwapArgs a, const int *pairs) {
+    const int i = pairs[2 * blockIdx.y], j = pairs[2 * blockIdx.y + 1];
+    const long long eP = a.sP, eG = a.sG, eN = 4LL * a.n, eM = 13LL * a.me, eS = (long long)(sizeof(Scal) / sizeof(double));
+    const long long total = eP + eG + eN + eM + eS;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        double *x, *y;
+        long long r = e;
+        if (r < eP) { x = a.P + i * a.sP + r; y = a.P + j * a.sP + r; }
+        else if ((r -= eP) < eG) { x = a.G + i * a.sG + r; y = a.G + j * a.sG + r; }
+        else if ((r -= eG) < eN) {
+            const long long arr = r / a.n, k = r % a.n;
+            double *base = a.vecs + arr * (long long)a.Btot * a.n;
+            x = base + (long long)i * a.n + k; y = base + (long long)j * a.n + k;
+        } else if ((r -= eN) < eM) {
+            const long long arr = r / a.me, k = r % a.me;
+            double *base = a.vecs + 4LL * a.Btot * a.n + arr * (long long)a.Btot * a.me;
+            x = base + (long long)i * a.me + k; y = base + (long long)j * a.me + k;
+        } else {
+            r -= eM;
+            x = reinterpret_cast<double *>(a.sc + i) + r; y = reinterpret_cast<double *>(a.sc + j) + r;
+        }
+        const double t = *x; *x = *y; *y = t;
+    }
+}
+// out[perm[slot], :] = in[slot, :]
+__global__ void k_unpermute_rows(const double *in, double *out, const int *perm, int len) {
+    const int slot = blockIdx.x;
+    const double *src = in + (long long)slot * len;
+    double *dst = out + (long long)perm[slot] * len;
+    for (int k = threadIdx.x; k < len; k += blockDim.x) dst[k] = src[k];
+}
+static_assert(sizeof(Scal) % sizeof(double) == 0, "Scal is swapped as doubles");
 // NT scaling at iteration 0 (misc.py:284-287) and lambda^2 (:2244)
 __global__ void k_scaling(Ptrs p, int first) {
     PB_SETUP
@@ -271,6 +316,11 @@ struct cvxb_batch {
     Ptrs p;
     Scal *sc = nullptr;
     int *d_info = nullptr, *d_ndone = nullptr;
+    int *d_done = nullptr, *d_pairs = nullptr, *d_perm = nullptr;     // compaction: done flags, swap list, slot -> problem
+    std::vector<int> perm;           // slot -> original problem index (identity unless the last solve compacted)
+    bool permuted = false;
+    int compact = 1;                 // CVXB_BATCH_COMPACT=0 disables
+    int Bact = 0;                    // slots [0, Bact) are launched by the lock-step loop
     CholWork cw;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -322,14 +372,14 @@ int batch_factor(cvxb_batch *b) {
     g.w = b->p.di2; g.sW = b->m;
     g.D = b->P; g.ldd = (int)b->ldp; g.sD = b->sP; g.beta = 1.0;
     g.C = b->K; g.ldc = (int)b->ldk; g.sC = b->sK;
-    g.lower_only = true; g.batch = b->B;
+    g.lower_only = true; g.batch = b->Bact;
     if (b->B == 1) g.splitk_ws = b->cw.splitk_ws;
     CVXB_TRY(dmma_gemm(g, st));
     if (b->B == 1) {
         CVXB_TRY(potrf_lower(b->n, b->K, (int)b->ldk, b->inv, b->cw, st));
         CVXB_CUDA(cudaMemcpyAsync(b->d_info, b->cw.d_info, sizeof(int), cudaMemcpyDeviceToDevice, st));
     } else {
-        CVXB_TRY(potrf_lower_batched(b->n, b->K, (int)b->ldk, b->sK, b->inv, b->sInv, b->B, b->d_info,
+        CVXB_TRY(potrf_lower_batched(b->n, b->K, (int)b->ldk, b->sK, b->inv, b->sInv, b->Bact, b->d_info,
                                      b->panel, (b->n + 1) & ~1, st));
     }
     return 0;
@@ -338,7 +388,7 @@ int batch_factor(cvxb_batch *b) {
 // (dx, bzp) := solution of the reduced KKT system; on entry dx = bx, bzp = W^{-T} bz
 int batch_solve(cvxb_batch *b) {
     cudaStream_t st = b->st;
-    const int n = b->n, m = b->m, B = b->B;
+    const int n = b->n, m = b->m, B = b->Bact;
     GemvBatch gt; gt.batch = B; gt.sA = b->sG; gt.sw = m; gt.sx = m; gt.sy = n;
     // x := x + G' (di .* bzp)
     CVXB_TRY(gemv_t(m, n, b->G, b->ldg, b->p.di, b->p.bzp, 1.0, 1.0, b->p.dx, st, gt));
@@ -404,6 +454,12 @@ int cvxb_batch_create(cvxb_batch **out, int nprob, int n, int m, int device) {
     b->p.sc = b->sc;
     BCUDA(cudaMalloc(&b->d_info, B * sizeof(int)));
     BCUDA(cudaMalloc(&b->d_ndone, sizeof(int)));
+    BCUDA(cudaMalloc(&b->d_done, B * sizeof(int)));
+    BCUDA(cudaMalloc(&b->d_pairs, 2 * B * sizeof(int)));
+    BCUDA(cudaMalloc(&b->d_perm, B * sizeof(int)));
+    b->perm.resize(B);
+    for (size_t i = 0; i < B; ++i) b->perm[i] = (int)i;
+    if (const char *e = getenv("CVXB_BATCH_COMPACT")) b->compact = (e[0] == '0') ? 0 : 1;
 #undef BCUDA
     *out = b;
     return 0;
@@ -419,6 +475,9 @@ void cvxb_batch_destroy(cvxb_batch *b) {
     if (b->oz_work) cudaFree(b->oz_work);
     if (b->d_info) cudaFree(b->d_info);
     if (b->d_ndone) cudaFree(b->d_ndone);
+    if (b->d_done) cudaFree(b->d_done);
+    if (b->d_pairs) cudaFree(b->d_pairs);
+    if (b->d_perm) cudaFree(b->d_perm);
     chol_work_destroy(b->cw);
     if (b->e0) cudaEventDestroy(b->e0);
     if (b->e1) cudaEventDestroy(b->e1);
@@ -446,6 +505,39 @@ int cvxb_batch_load(cvxb_batch *b, const double *P, const double *q, const doubl
     CVXB_TRY(symmetrize_lower(b->n, b->P, b->ldp, b->B, b->sP, b->st));
     CVXB_CUDA(cudaStreamSynchronize(b->st));
     b->loaded = true;
+    for (size_t i = 0; i < B; ++i) b->perm[i] = (int)i;
+    b->permuted = false;
+    return 0;
+}
+
+// swap the slots of each pair (disjoint pairs: one launch)
+static int swap_slots(cvxb_batch *b, const std::vector<int> &pairs) {
+    const int np = (int)pairs.size() / 2;
+    if (np == 0) return 0;
+    CVXB_CUDA(cudaMemcpyAsync(b->d_pairs, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice, b->st));
+    SwapArgs a;
+    a.P = b->P; a.G = b->G; a.vecs = b->vecs; a.sc = b->sc; a.sP = b->sP; a.sG = b->sG;
+    a.n = b->n; a.me = b->m > 0 ? b->m : 1; a.Btot = b->B;
+    k_swap_slots<<<dim3(96, np), 256, 0, b->st>>>(a, b->d_pairs);
+    count_launch();
+    // `pairs` is pageable host memory: the copy above is staged before cudaMemcpyAsync returns
+    return 0;
+}
+
+// put every problem back into its own slot (a solve that compacted left them permuted)
+static int restore_order(cvxb_batch *b) {
+    if (!b->permuted) return 0;
+    std::vector<int> pr(2);
+    for (int i = 0; i < b->B; ++i) {
+        while (b->perm[i] != i) {
+            const int j = b->perm[i];                // the problem in slot i belongs to slot j
+            pr[0] = i; pr[1] = j;
+            CVXB_TRY(swap_slots(b, pr));
+            std::swap(b->perm[i], b->perm[j]);
+        }
+    }
+    CVXB_CUDA(cudaStreamSynchronize(b->st));
+    b->permuted = false;
     return 0;
 }
 
@@ -453,11 +545,15 @@ int cvxb_batch_solve(cvxb_batch *b, int maxiters, double abstol, double reltol, 
     if (!b || !b->loaded) { set_error("batch_solve: load the problems first"); return CVXB_E_ARG; }
     CVXB_CUDA(cudaSetDevice(b->device));
     cudaStream_t st = b->st;
-    const int B = b->B, n = b->n, m = b->m, T = 256;
+    CVXB_TRY(restore_order(b));
+    const int n = b->n, m = b->m, T = 256;
+    int B = b->B;                                 // active slots: shrinks as problems finish (compaction)
+    b->Bact = B;
     Ptrs &p = b->p;
     GemvBatch gP; gP.batch = B; gP.sA = b->sP; gP.sx = n; gP.sy = n;
     GemvBatch gGt; gGt.batch = B; gGt.sA = b->sG; gGt.sx = m; gGt.sy = n;
     GemvBatch gGn; gGn.batch = B; gGn.sA = b->sG; gGn.sx = n; gGn.sy = m;
+    CVXB_CUDA(cudaMemsetAsync(b->sc, 0, (size_t)B * sizeof(Scal), st));
     CVXB_CUDA(cudaEventRecord(b->e0, st));
     // ---- starting point: W = I ----
     k_init_rhs<<<B, T, 0, st>>>(p); count_launch();
@@ -478,6 +574,7 @@ int cvxb_batch_solve(cvxb_batch *b, int maxiters, double abstol, double reltol, 
             return CVXB_E_ARG;
         }
     }
+    std::vector<int> flags(B), pairs;
     int it = 0;
     for (it = 0; it <= maxiters; ++it) {
         // residuals (:2169-2186)
@@ -489,11 +586,30 @@ int cvxb_batch_solve(cvxb_batch *b, int maxiters, double abstol, double reltol, 
             CVXB_TRY(gemv_n(m, n, b->G, b->ldg, nullptr, p.x, 1.0, 1.0, p.rz, b->gemv_ws, st, gGn));
         }
         CVXB_CUDA(cudaMemsetAsync(b->d_ndone, 0, sizeof(int), st));
-        k_stats<<<B, T, 0, st>>>(p, it, maxiters, abstol, reltol, feastol, b->d_ndone); count_launch();
+        k_stats<<<B, T, 0, st>>>(p, it, maxiters, abstol, reltol, feastol, b->d_ndone, b->d_done); count_launch();
         int ndone = 0;
         CVXB_CUDA(cudaMemcpyAsync(&ndone, b->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CVXB_CUDA(cudaMemcpyAsync(flags.data(), b->d_done, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
         CVXB_CUDA(cudaStreamSynchronize(st));
         if (ndone >= B) break;
+        if (ndone > 0 && b->compact && b->B > 1) {
+            // finished slots below the new active count trade places with active slots from the tail
+            const int nb = B - ndone;
+            pairs.clear();
+            int j = B - 1;
+            for (int i = 0; i < nb; ++i) {
+                if (!flags[i]) continue;
+                while (flags[j]) --j;             // an active slot in [nb, B): there are as many as finished ones below nb
+                pairs.push_back(i); pairs.push_back(j);
+                std::swap(b->perm[i], b->perm[j]);
+                --j;
+            }
+            CVXB_TRY(swap_slots(b, pairs));
+            b->permuted = true;
+            B = nb;
+            b->Bact = B;
+            gP.batch = gGt.batch = gGn.batch = B;
+        }
         k_scaling<<<B, T, 0, st>>>(p, it == 0 ? 1 : 0); count_launch();
         CVXB_TRY(batch_factor(b));
         for (int i = 0; i < 2; ++i) {
@@ -505,6 +621,7 @@ int cvxb_batch_solve(cvxb_batch *b, int maxiters, double abstol, double reltol, 
         CVXB_LAUNCH_CHECK();
     }
     b->iters_run = it;
+    b->Bact = b->B;
     CVXB_CUDA(cudaEventRecord(b->e1, st));
     CVXB_CUDA(cudaStreamSynchronize(st));
     float t = 0;
@@ -519,18 +636,33 @@ int cvxb_batch_results(cvxb_batch *b, double *x, double *s, double *z, int *stat
     CVXB_CUDA(cudaSetDevice(b->device));
     const cudaMemcpyKind kind = (space == CVXB_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     const size_t B = b->B;
-    if (x) CVXB_CUDA(cudaMemcpy(x, b->p.x, B * b->n * sizeof(double), kind));
-    if (s && b->m) CVXB_CUDA(cudaMemcpy(s, b->p.s, B * b->m * sizeof(double), kind));
-    if (z && b->m) CVXB_CUDA(cudaMemcpy(z, b->p.z, B * b->m * sizeof(double), kind));
+    // slot -> problem (identity unless the solve compacted finished problems away)
+    if (b->permuted) CVXB_CUDA(cudaMemcpy(b->d_perm, b->perm.data(), B * sizeof(int), cudaMemcpyHostToDevice));
+    auto give = [&](double *dst, const double *src, int len) -> int {
+        if (!b->permuted) { CVXB_CUDA(cudaMemcpy(dst, src, B * len * sizeof(double), kind)); return 0; }
+        double *tmp = (space == CVXB_DEVICE) ? dst : nullptr;
+        if (!tmp) CVXB_CUDA(tmp_malloc(&tmp, B * len * sizeof(double)));
+        k_unpermute_rows<<<(unsigned)B, 256, 0, b->st>>>(src, tmp, b->d_perm, len);
+        count_launch();
+        cudaError_t e = cudaStreamSynchronize(b->st);
+        if (e == cudaSuccess && tmp != dst) e = cudaMemcpy(dst, tmp, B * len * sizeof(double), kind);
+        if (tmp != dst) tmp_free(tmp);
+        CVXB_CUDA(e);
+        return 0;
+    };
+    if (x) CVXB_TRY(give(x, b->p.x, b->n));
+    if (s && b->m) CVXB_TRY(give(s, b->p.s, b->m));
+    if (z && b->m) CVXB_TRY(give(z, b->p.z, b->m));
     if (status || iters || pobj || dobj) {
         if (space == CVXB_DEVICE) { set_error("batch_results: scalars are returned to host memory only"); return CVXB_E_ARG; }
         std::vector<Scal> sc(B);
         CVXB_CUDA(cudaMemcpy(sc.data(), b->sc, B * sizeof(Scal), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < B; ++i) {
-            if (status) status[i] = sc[i].status;
-            if (iters) iters[i] = sc[i].iters;
-            if (pobj) pobj[i] = sc[i].pcost;
-            if (dobj) dobj[i] = sc[i].dcost;
+        for (size_t slot = 0; slot < B; ++slot) {
+            const size_t i = (size_t)b->perm[slot];
+            if (status) status[i] = sc[slot].status;
+            if (iters) iters[i] = sc[slot].iters;
+            if (pobj) pobj[i] = sc[slot].pcost;
+            if (dobj) dobj[i] = sc[slot].dcost;
         }
     }
     return 0;

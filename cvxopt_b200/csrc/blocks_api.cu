@@ -57,9 +57,9 @@ int get_ctx(int device, CtxRef *out) {
 // RAII device temp
 struct DBuf {
     double *p = nullptr;
-    ~DBuf() { if (p) cudaFree(p); }
+    ~DBuf() { if (p) tmp_free(p); }
     int alloc(size_t n) {
-        CVXB_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(double)));
+        CVXB_CUDA(tmp_malloc(&p, (n ? n : 1) * sizeof(double)));
         return 0;
     }
 };
@@ -68,11 +68,11 @@ struct DBuf {
 // use the pointer directly (space == DEVICE)
 struct Staged {
     double *dev = nullptr; double *host = nullptr; size_t n = 0; bool owned = false;
-    ~Staged() { if (owned && dev) cudaFree(dev); }
+    ~Staged() { if (owned && dev) tmp_free(dev); }
     int in(const double *src, size_t count, int space, cudaStream_t st) {
         n = count; host = const_cast<double *>(src);
         if (space == CVXB_DEVICE) { dev = host; owned = false; return 0; }
-        CVXB_CUDA(cudaMalloc(&dev, (n ? n : 1) * sizeof(double)));
+        CVXB_CUDA(tmp_malloc(&dev, (n ? n : 1) * sizeof(double)));
         owned = true;
         if (n) CVXB_CUDA(cudaMemcpyAsync(dev, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
         return 0;
@@ -107,14 +107,14 @@ int cvxb_syrk_scaled_i8(int n, int k, const double *A, int lda, const double *d,
     CtxRef ctx; CVXB_TRY(get_ctx(device, &ctx));
     void *work = nullptr;
     if (slices < 1 || slices > 9) { set_error("syrk_scaled_i8: slices must be 1..9"); return CVXB_E_ARG; }
-    if (cudaMalloc(&work, ozaki_workspace_bytes(n, k, slices)) != cudaSuccess) {
+    if (tmp_malloc(&work, ozaki_workspace_bytes(n, k, slices)) != cudaSuccess) {
         cudaGetLastError();
         set_error("syrk_scaled_i8: out of device memory for the slice workspace");
         return CVXB_E_NOMEM;
     }
     int rc = ozaki_syrk(n, k, A, lda, d, H, ldh, 1.0, C, ldc, slices, 0, work, nullptr, ctx->st);
     cudaError_t e = cudaStreamSynchronize(ctx->st);
-    cudaFree(work);
+    tmp_free(work);
     if (rc) return rc;
     if (e != cudaSuccess) { set_error("syrk_scaled_i8: %s", cudaGetErrorString(e)); return CVXB_E_CUDA; }
     return 0;

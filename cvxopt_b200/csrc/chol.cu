@@ -74,6 +74,10 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
         unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));       \
         trace[8 * 2048 + (SLOT)] = t_;                                                      \
     }
+    // Programmatic dependent launch (CVXB_CHOL_PDL): the next diagonal-block kernel of the chain may be scheduled while
+    // this one runs; it blocks here until its predecessor has completed and flushed.  No-ops for ordinary launches.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     A += (long long)blockIdx.x * sA; inv += (long long)blockIdx.x * sInv;
     invT += (long long)blockIdx.x * sInv; info += blockIdx.x;
     double *M = sm;                    // NB x LDM, column-major
@@ -98,27 +102,49 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
 #pragma unroll
             for (int rf = 0; rf < 8; ++rf) acc[cf][rf][0] = acc[cf][rf][1] = 0.0;
         const int kkmax = (wc + 1) * 8;                 // invprev[c, k] = 0 for k > c
-        const double *tp[8];
-        bool tv[8];
-#pragma unroll
-        for (int rf = 0; rf < 8; ++rf) {
-            const int r = wr * 64 + rf * 8 + g4;
-            tv[rf] = r < jb;
-            tp[rf] = Tprev + (tv[rf] ? r : 0) + (long long)t4 * ldt;
+        // Tprev (jb x 128) goes to shared memory M in one burst of async copies: read straight from global memory in
+        // the k loop, the loop was a chain of L2 round trips (6 us for 0.5 MFLOP per warp)
+        {
+            const bool v16 = ((ldt & 1) == 0) && ((reinterpret_cast<uintptr_t>(Tprev) & 15) == 0);
+            if (v16) {
+                for (int q = tid; q < NB * NB / 2; q += 256) {
+                    const int c = q >> 6, r = (q & 63) * 2;
+                    const int nb = (r + 1 < jb) ? 16 : (r < jb ? 8 : 0);
+                    cp_async16(M + r + c * LDM, nb ? Tprev + r + (long long)c * ldt : Tprev, nb);
+                }
+            } else {
+                for (int q = tid; q < NB * NB; q += 256) {
+                    const int c = q >> 7, r = q & 127;
+                    cp_async8(M + r + c * LDM, (r < jb) ? Tprev + r + (long long)c * ldt : Tprev, (r < jb) ? 8 : 0);
+                }
+            }
+            cp_async_commit();
         }
         const double *ip = invprev + (wc * 32 + g4) + t4 * NB;
+        // first fragments of inv(L_prev) while the copies are in flight
+        double a0[4];
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) a0[cf] = ip[cf * 8];
+        cp_async_wait<0>();
+        __syncthreads();
+        const double *tq = M + (wr * 64 + g4) + t4 * LDM;
 #pragma unroll 2
         for (int kk = 0; kk < kkmax; ++kk) {
             double a[4], bfr[8];
 #pragma unroll
-            for (int cf = 0; cf < 4; ++cf) a[cf] = ip[cf * 8 + kk * 4 * NB];
+            for (int cf = 0; cf < 4; ++cf) a[cf] = a0[cf];
+            if (kk + 1 < kkmax) {
 #pragma unroll
-            for (int rf = 0; rf < 8; ++rf) bfr[rf] = tv[rf] ? tp[rf][(long long)kk * 4 * ldt] : 0.0;
+                for (int cf = 0; cf < 4; ++cf) a0[cf] = ip[cf * 8 + (kk + 1) * 4 * NB];
+            }
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) bfr[rf] = tq[rf * 8 + kk * 4 * LDM];
 #pragma unroll
             for (int cf = 0; cf < 4; ++cf)
 #pragma unroll
                 for (int rf = 0; rf < 8; ++rf) dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bfr[rf]);
         }
+        __syncthreads();                                // every warp is done reading Tprev from M
 #pragma unroll
         for (int cf = 0; cf < 4; ++cf)
 #pragma unroll
@@ -658,7 +684,9 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         // ---- D: diagonal block.  Needs A(jb,jb) updated through panel jb-2 and the raw tile A(jb,jb-1)
         // (block column jb-1 complete through panel jb-2): C0(jb-2) [which follows D0(jb-2) on T] and the
         // last bulk update that touched block column jb.
-        if (jb >= 2) {
+        static int nowait = -1;      // timing experiment only (WRONG results): chain stream without its cross-stream waits
+        if (nowait < 0) { const char *e = getenv("CVXB_CHOL_NOWAIT_EXPERIMENT"); nowait = (e && e[0] == '1') ? 1 : 0; }
+        if (jb >= 2 && !nowait) {
             CVXB_CUDA(cudaStreamWaitEvent(D, w.ev_c0[jb - 2], 0));
             // the latest bulk update issued at a step <= jb-2 (a later one belongs to panels the prologue
             // applies itself, waiting for it would serialise the chain behind the bulk work)
@@ -669,8 +697,24 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
         }
         const double *Tprev = jb > 0 ? A + j + (long long)(j - NB) * lda : nullptr;
         const double *invprev = jb > 0 ? inv + (long long)(jb - 1) * NB * NB : nullptr;
-        potf2_inv_kernel<<<1, 256, POTF2_SMEM, D>>>(Ajj, lda, wj, invj, invTj, w.d_info, j, 0, 0, Tprev,
-                                                     lda, invprev, w.trace ? w.trace + 8 * jb : nullptr);
+        static int pdl = -1;
+        if (pdl < 0) { const char *e = getenv("CVXB_CHOL_PDL"); pdl = (e && e[0] == '1') ? 1 : 0; }
+        if (pdl && jb > 0) {
+            // the edge potf2(jb-1) -> potf2(jb) on the chain stream becomes a programmatic dependency: the launch
+            // latency (~10 us of the ~107 us per chain step, profiles/r01_potrf_timeline.md) overlaps the predecessor
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = POTF2_SMEM; cfg.stream = D;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            unsigned long long *tr = w.trace ? w.trace + 8 * jb : nullptr;
+            CVXB_CUDA(cudaLaunchKernelEx(&cfg, potf2_inv_kernel, Ajj, (long long)lda, wj, invj, invTj, w.d_info, j,
+                                         (long long)0, (long long)0, Tprev, (long long)lda, invprev, tr));
+        } else {
+            potf2_inv_kernel<<<1, 256, POTF2_SMEM, D>>>(Ajj, lda, wj, invj, invTj, w.d_info, j, 0, 0, Tprev,
+                                                         lda, invprev, w.trace ? w.trace + 8 * jb : nullptr);
+        }
         count_launch();
         CVXB_LAUNCH_CHECK();
         CVXB_CUDA(cudaEventRecord(w.ev_dg[jb], D));

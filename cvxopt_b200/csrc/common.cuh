@@ -56,6 +56,18 @@ struct DeviceOnce {
         }                                                                          \
     } while (0)
 
+// ---- scratch-buffer cache ----------------------------------------------------
+// The cone / scaling entry points (cvxb_scale, cvxb_max_step, cvxb_update_scaling ...) need device temporaries per call;
+// cudaMalloc + cudaFree cost 0.1-1 ms each (cudaFree also synchronises the device), which was most of a call
+// (profiles/r02t: 10.6 ms per cvxb_scale on a 512 x 512 's' block whose GEMMs take 0.1 ms).  tmp_malloc / tmp_free keep
+// freed blocks per device and hand them out again (best fit within +25 %); callers synchronise their stream before
+// freeing, as they did for cudaFree.  The cache is bounded (CVXB_TMP_CACHE_MB, default 4096) and is dropped when a
+// real allocation fails.
+cudaError_t tmp_malloc_bytes(void **p, size_t bytes);
+void tmp_free(void *p);
+void tmp_cache_release();          // free every cached block of every device
+template <class T> inline cudaError_t tmp_malloc(T **p, size_t bytes) { return tmp_malloc_bytes(reinterpret_cast<void **>(p), bytes); }
+
 constexpr int kNumSMs = 148;       // B200: 2 dies x 74 SMs
 constexpr int NB = 128;            // Cholesky block size == GEMM tile edge
 

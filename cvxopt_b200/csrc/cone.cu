@@ -34,7 +34,7 @@ int ConeLayout::init(const cvxb_dims *dims) {
     cdim_pckd = mnl + ml + sumq + sump;
     auto up = [&](int **dst, const std::vector<int> &h) -> int {
         if (h.empty()) { *dst = nullptr; return 0; }
-        CVXB_CUDA(cudaMalloc(dst, h.size() * sizeof(int)));
+        CVXB_CUDA(tmp_malloc(dst, h.size() * sizeof(int)));
         CVXB_CUDA(cudaMemcpy(*dst, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
         return 0;
     };
@@ -46,13 +46,13 @@ int ConeLayout::init(const cvxb_dims *dims) {
 
 void ConeLayout::destroy() {
     int **ptrs[] = {&d_q, &d_qoff, &d_voff, &d_s, &d_soff, &d_spoff, &d_roff};
-    for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+    for (auto pp : ptrs) { if (*pp) tmp_free(*pp); *pp = nullptr; }
 }
 
 // ------------------------------------------------------------------ scaling storage
 int DevScaling::alloc(const ConeLayout &c) {
     total = (size_t)2 * c.mnl + (size_t)3 * c.ml + c.sumq + c.nq + (size_t)2 * c.sums2 + 8;
-    CVXB_CUDA(cudaMalloc(&store, total * sizeof(double)));
+    CVXB_CUDA(tmp_malloc(&store, total * sizeof(double)));
     CVXB_CUDA(cudaMemset(store, 0, total * sizeof(double)));
     double *p = store;
     dnl = p; p += c.mnl; dnli = p; p += c.mnl;
@@ -61,7 +61,7 @@ int DevScaling::alloc(const ConeLayout &c) {
     r = p; p += c.sums2; rti = p; p += c.sums2;
     return 0;
 }
-void DevScaling::destroy() { if (store) cudaFree(store); store = nullptr; }
+void DevScaling::destroy() { if (store) tmp_free(store); store = nullptr; }
 cvxb_scaling DevScaling::view() const {
     cvxb_scaling w;
     w.dnl = dnl; w.dnli = dnli; w.d = d; w.di = di; w.v = v; w.beta = beta; w.r = r; w.rti = rti;

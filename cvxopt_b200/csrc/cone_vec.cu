@@ -7,6 +7,7 @@
 // plane rotations at once, one thread per 2x2 block of J'AJ, ping-ponging between two copies so a
 // round is a single race-free pass.
 #include "cone.cuh"
+#include <cooperative_groups.h>
 #include <mutex>
 #include <map>
 #include <vector>
@@ -284,10 +285,29 @@ __global__ void jac_init_kernel(JacArgs a) {
 template <bool WITH_V>
 __global__ void jac_round_kernel(JacArgs a, int r, int flip) {
     const int k = blockIdx.z, mk = a.s[k];
-    const int I = blockIdx.y * blockDim.y + threadIdx.y, J = blockIdx.x * blockDim.x + threadIdx.x;
+    // I (the row pair) is the fast thread index: consecutive I are consecutive rows of the column-major blocks
+    const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= a.N / 2 || J >= a.N / 2) return;
     const size_t o = a.soff[k];
     jac_block<WITH_V>((flip ? a.w1 : a.w0) + o, (flip ? a.w0 : a.w1) + o, a.V + (WITH_V ? o : 0), mk, a.N, r, I, J);
+}
+
+// A whole sweep (N - 1 rounds) in one cooperative launch, a grid barrier between rounds; the buffers swap every round,
+// so the result of the sweep is in the buffer the sweep did NOT start from (N - 1 is odd).
+template <bool WITH_V>
+__global__ void __launch_bounds__(256) jac_sweep_kernel(JacArgs a, int flip) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int k = blockIdx.z, mk = a.s[k];
+    const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y * blockDim.y + threadIdx.y;
+    const bool live = I < a.N / 2 && J < a.N / 2;
+    const size_t o = a.soff[k];
+    for (int r = 0; r < a.N - 1; ++r) {
+        if (live)
+            jac_block<WITH_V>((flip ? a.w1 : a.w0) + o, (flip ? a.w0 : a.w1) + o, a.V + (WITH_V ? o : 0), mk, a.N, r, I, J);
+        grid.sync();
+        flip ^= 1;
+    }
 }
 
 __global__ void jac_off_kernel(JacArgs a, int flip) {
@@ -352,7 +372,7 @@ __global__ void __launch_bounds__(1024) jac_small_kernel(JacArgs a, int max_swee
     }
     __syncthreads();
     const int N = max(2, mk + (mk & 1)), h = N / 2;
-    const int I = tid / h, J = tid % h;
+    const int I = tid % h, J = tid / h;          // I fastest: rows of the column-major block
     double prev = 1e300;
     int sweep = 0;
     bool ok = false;
@@ -368,7 +388,7 @@ __global__ void __launch_bounds__(1024) jac_small_kernel(JacArgs a, int max_swee
         if (sweep == max_sweeps) break;
         prev = off;
         for (int r = 0; r < N - 1; ++r) {
-            if (I < h) jac_block<WITH_V>(w0, w1, V, mk, N, r, I, J);
+            if (J < h) jac_block<WITH_V>(w0, w1, V, mk, N, r, I, J);
             __syncthreads();
             double *t = w0; w0 = w1; w1 = t;
         }
@@ -420,11 +440,11 @@ int vctx(cudaStream_t *st) {
 
 struct Buf {       // host buffer staged on the device (or a device pointer used in place)
     double *dev = nullptr, *host = nullptr; size_t n = 0; bool owned = false;
-    ~Buf() { if (owned && dev) cudaFree(dev); }
+    ~Buf() { if (owned && dev) tmp_free(dev); }
     int in(const double *src, size_t count, int space, cudaStream_t st) {
         n = count; host = const_cast<double *>(src);
         if (space == CVXB_DEVICE) { dev = host; return 0; }
-        CVXB_CUDA(cudaMalloc(&dev, (n ? n : 1) * sizeof(double)));
+        CVXB_CUDA(tmp_malloc(&dev, (n ? n : 1) * sizeof(double)));
         owned = true;
         if (n) CVXB_CUDA(cudaMemcpyAsync(dev, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
         return 0;
@@ -482,7 +502,7 @@ int cvxb_sprod(double *x, const double *y, const cvxb_dims *dims, int diag, int 
             if (mk == 0) continue;
             const long long m2 = (long long)mk * mk;
             double *tmp = nullptr;
-            CVXB_CUDA(cudaMalloc(&tmp, 3 * m2 * sizeof(double)));
+            CVXB_CUDA(tmp_malloc(&tmp, 3 * m2 * sizeof(double)));
             double *As = tmp, *Ys = tmp + m2, *T = tmp + 2 * m2;
             int rc = 0;
             do {
@@ -500,7 +520,7 @@ int cvxb_sprod(double *x, const double *y, const cvxb_dims *dims, int diag, int 
                 count_launch();
             } while (0);
             cudaStreamSynchronize(st);
-            cudaFree(tmp);
+            tmp_free(tmp);
             if (rc) return rc;
         }
     }
@@ -545,12 +565,12 @@ int cvxb_sdot(const double *x, const double *y, const cvxb_dims *dims, double *r
     CVXB_TRY(xb.in(x, L.c.cdim, space, st));
     CVXB_TRY(yb.in(y, L.c.cdim, space, st));
     double *d = nullptr;
-    CVXB_CUDA(cudaMalloc(&d, sizeof(double)));
+    CVXB_CUDA(tmp_malloc(&d, sizeof(double)));
     sdot_kernel<<<1, 256, 0, st>>>(xb.dev, yb.dev, L.k, L.c.mnl + L.c.ml + L.c.sumq, d);
     count_launch();
     cudaError_t e = cudaMemcpyAsync(result, d, sizeof(double), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
-    cudaFree(d);
+    tmp_free(d);
     if (e != cudaSuccess) { set_error("sdot: %s", cudaGetErrorString(e)); return CVXB_E_CUDA; }
     return 0;
 }
@@ -571,13 +591,13 @@ static int sym_eig_blocks(const ConeLayout &c, double *xs, double *sigma_dev, co
     int rc = 0;
     auto done = [&](int r) {
         cudaStreamSynchronize(st);
-        cudaFree(work); cudaFree(stats); cudaFree(perm); cudaFree(fail);
+        tmp_free(work); tmp_free(stats); tmp_free(perm); tmp_free(fail);
         return r;
     };
-    if (cudaMalloc(&work, (with_vectors ? 3 : 2) * m2 * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&stats, 2 * (size_t)c.ns * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&perm, (size_t)(sums ? sums : 1) * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&fail, sizeof(int)) != cudaSuccess) {
+    if (tmp_malloc(&work, (with_vectors ? 3 : 2) * m2 * sizeof(double)) != cudaSuccess ||
+        tmp_malloc(&stats, 2 * (size_t)c.ns * sizeof(double)) != cudaSuccess ||
+        tmp_malloc(&perm, (size_t)(sums ? sums : 1) * sizeof(int)) != cudaSuccess ||
+        tmp_malloc(&fail, sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         set_error("max_step: out of device memory for the eigensolver workspace");
         return done(CVXB_E_NOMEM);
@@ -608,6 +628,19 @@ static int sym_eig_blocks(const ConeLayout &c, double *xs, double *sigma_dev, co
     }
     int flip = 0;
     bool ok = false;
+    // one cooperative launch per sweep when all its CTAs can be resident at once (CVXB_JACOBI_COOP=0: per-round launches)
+    bool coop = false;
+    {
+        static int coop_on = -1;
+        if (coop_on < 0) { const char *e = getenv("CVXB_JACOBI_COOP"); coop_on = (e && e[0] == '0') ? 0 : 1; }
+        int dev = 0, can = 0, per_sm = 0, sms = 0;
+        const void *fn = with_vectors ? (const void *)jac_sweep_kernel<true> : (const void *)jac_sweep_kernel<false>;
+        if (coop_on && cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && can &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) == cudaSuccess)
+            coop = (long long)per_sm * sms >= (long long)((h + 15) / 16) * ((h + 15) / 16) * c.ns;
+    }
     for (int sweep = 0; sweep <= MAX_SWEEPS; ++sweep) {
         jac_off_kernel<<<c.ns, 256, 0, st>>>(a, flip);
         count_launch();
@@ -621,11 +654,22 @@ static int sym_eig_blocks(const ConeLayout &c, double *xs, double *sigma_dev, co
         }
         if (ok || sweep == MAX_SWEEPS) break;
         const dim3 blk(16, 16), grd((h + 15) / 16, (h + 15) / 16, c.ns);
-        for (int r = 0; r < a.N - 1; ++r) {
-            if (with_vectors) jac_round_kernel<true><<<grd, blk, 0, st>>>(a, r, flip);
-            else jac_round_kernel<false><<<grd, blk, 0, st>>>(a, r, flip);
+        if (coop) {
+            void *args[] = {&a, &flip};
+            const void *fn = with_vectors ? (const void *)jac_sweep_kernel<true> : (const void *)jac_sweep_kernel<false>;
+            if (cudaLaunchCooperativeKernel(fn, grd, blk, args, 0, st) != cudaSuccess) {
+                set_error("max_step: cooperative launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return done(CVXB_E_CUDA);
+            }
             count_launch();
-            flip ^= 1;
+            flip ^= 1;                                   // N - 1 (odd) buffer swaps
+        } else {
+            for (int r = 0; r < a.N - 1; ++r) {
+                if (with_vectors) jac_round_kernel<true><<<grd, blk, 0, st>>>(a, r, flip);
+                else jac_round_kernel<false><<<grd, blk, 0, st>>>(a, r, flip);
+                count_launch();
+                flip ^= 1;
+            }
         }
     }
     if (!ok) { set_error("max_step: Jacobi eigensolver did not converge (non-finite input?)"); return done(1); }
@@ -653,15 +697,15 @@ int cvxb_max_step(double *x, const cvxb_dims *dims, double *sigma, double *resul
     CVXB_TRY(xb.in(x, L.c.cdim, space, st));
     double *d = nullptr, *dsig = nullptr;
     int *dsigoff = nullptr;
-    auto done = [&](int r) { cudaFree(d); cudaFree(dsig); cudaFree(dsigoff); return r; };
-    CVXB_CUDA(cudaMalloc(&d, sizeof(double)));
+    auto done = [&](int r) { tmp_free(d); tmp_free(dsig); tmp_free(dsigoff); return r; };
+    CVXB_CUDA(tmp_malloc(&d, sizeof(double)));
     max_step_kernel<<<1, 256, 0, st>>>(xb.dev, L.k, d);
     count_launch();
     if (L.c.maxs > 0) {
         // 's' blocks: lambda_min of each block (reference dsyevr_ range 'I' 1..1, or dsyevd_ 'V' when
         // sigma is given: eigenvalues -> sigma, eigenvectors -> x; misc_solvers.c:1099-1150)
-        if (cudaMalloc(&dsig, (size_t)sums * sizeof(double)) != cudaSuccess ||
-            cudaMalloc(&dsigoff, (size_t)L.c.ns * sizeof(int)) != cudaSuccess ||
+        if (tmp_malloc(&dsig, (size_t)sums * sizeof(double)) != cudaSuccess ||
+            tmp_malloc(&dsigoff, (size_t)L.c.ns * sizeof(int)) != cudaSuccess ||
             cudaMemcpyAsync(dsigoff, sigoff.data(), (size_t)L.c.ns * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess) {
             cudaGetLastError();
             set_error("max_step: device allocation failed");

@@ -239,10 +239,31 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
     }
 
     double acc[4][8][2];
+    // Read-modify-write launches with alpha = +-1 (the Cholesky trailing updates: C = D - X Y'): full interior tiles
+    // start their accumulators from (beta/alpha) * D, loaded here straight into the fragment layout, so the loads
+    // complete under the main loop and the epilogue is stores only.  (Staging D through shared memory after the main
+    // loop cost a barrier, a 64 KB cp.async burst and its latency per tile: ~2 us of a ~10 us tile at K = 128.)
+    const bool pre_d = p.vec_c && (nr == BR) && (nc == BC) && !(p.lower_only && (c0 + BC - 1 > r0)) && !is_split &&
+                       p.beta != 0.0 && p.D != nullptr && (p.alpha == 1.0 || p.alpha == -1.0) && ((p.ldd & 1) == 0);
+    if (pre_d) {
+        const double sc = p.beta / p.alpha;
+        const double *Dt = p.D + b * p.sD + r0 + (long long)c0 * p.ldd;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int cf = 0; cf < 4; ++cf) {
+            const int cl = wc * 32 + cf * 8 + g4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int rf = 0; rf < 8; ++rf) {
+                const int rl = wr * 64 + rf * 8 + t4 * 2;
+                const double2 dv = *reinterpret_cast<const double2 *>(Dt + rl + (long long)cl * p.ldd);
+                acc[cf][rf][0] = sc * dv.x; acc[cf][rf][1] = sc * dv.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
 
     const int ktiles = (kend - kbeg + BK - 1) / BK;
     // lower-triangular outputs: a warp whose whole block is above the diagonal only helps with the
@@ -363,6 +384,18 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
     const bool fast = p.vec_c && (nr == BR) && (nc == BC) && !diag;
     if (fast) {
         // full interior tile, 16-byte accesses
+        if (pre_d) {
+#pragma unroll
+            for (int cf = 0; cf < 4; ++cf) {
+                const long long c = c0 + wc * 32 + cf * 8 + g4;
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) {
+                    double2 v = make_double2(p.alpha * acc[cf][rf][0], p.alpha * acc[cf][rf][1]);
+                    *reinterpret_cast<double2 *>(C + (r0 + wr * 64 + rf * 8 + t4 * 2) + c * p.ldc) = v;
+                }
+            }
+            return;
+        }
         if (use_d) {
             // read-modify-write epilogue: stage the whole D tile through the (now idle) pipeline
             // buffers with one burst of cp.async — a single memory round trip with coalesced
@@ -405,11 +438,24 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
         }
         return;
     }
+    // edge / diagonal tiles: the 16 values of D a thread needs per column fragment are loaded as one batch
+    // (C may alias D, so a load after a store cannot be hoisted: element-by-element this was 64 dependent round trips)
 #pragma unroll
     for (int cf = 0; cf < 4; ++cf) {
         const int cl = wc * 32 + cf * 8 + g4;
         if (cl >= nc) continue;
         const long long c = c0 + cl;
+        double dv[8][2];
+#pragma unroll
+        for (int rf = 0; rf < 8; ++rf) {
+            const int rl = wr * 64 + rf * 8 + t4 * 2;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long long r = r0 + rl + e;
+                const bool ok = use_d && (rl + e < nr) && !(diag && r < c);
+                dv[rf][e] = ok ? D[r + c * p.ldd] : 0.0;
+            }
+        }
 #pragma unroll
         for (int rf = 0; rf < 8; ++rf) {
             const int rl = wr * 64 + rf * 8 + t4 * 2;
@@ -419,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, 2) dmma_gemm_kernel(const KParams p) 
                 const long long r = r0 + rl + e;
                 if (diag && r < c) continue;
                 double v = p.alpha * acc[cf][rf][e];
-                if (use_d) v += p.beta * D[r + c * p.ldd];
+                if (use_d) v += p.beta * dv[rf][e];
                 C[r + c * p.ldc] = v;
             }
         }

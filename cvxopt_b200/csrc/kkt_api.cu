@@ -10,10 +10,107 @@
 #include <cstdarg>
 #include <mutex>
 
+#include <map>
+#include <unordered_map>
+#include <mutex>
+#include <iterator>
+#include <cstdlib>
+
 namespace cvxb {
 
 static thread_local std::string g_err;
 std::atomic<unsigned long long> g_launches{0};
+
+
+// ---- scratch-buffer cache (common.cuh) ----
+namespace {
+struct TmpCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_[64];          // per device: block size -> pointer
+    std::unordered_map<void *, std::pair<size_t, int>> live;   // handed-out blocks: size, device
+    size_t cached = 0, cap = 0;
+    bool cap_set = false;
+};
+TmpCache &tmpc() { static TmpCache *c = new TmpCache; return *c; }   // never destroyed: frees may come after main()
+size_t tmp_round(size_t b) { return b <= 4096 ? 4096 : (b + 65535) & ~(size_t)65535; }
+void tmp_drop_all_locked(TmpCache &c) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) {
+        if (c.free_[d].empty()) continue;
+        cudaSetDevice(d);
+        for (auto &kv : c.free_[d]) cudaFree(kv.second);
+        c.free_[d].clear();
+    }
+    cudaSetDevice(cur);
+    c.cached = 0;
+}
+}  // namespace
+
+cudaError_t tmp_malloc_bytes(void **p, size_t bytes) {
+    TmpCache &c = tmpc();
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const size_t want = tmp_round(bytes ? bytes : 1);
+    std::lock_guard<std::mutex> g(c.mu);
+    auto &fl = c.free_[dev & 63];
+    auto it = fl.lower_bound(want);
+    if (it != fl.end() && it->first <= want + want / 4) {
+        *p = it->second;
+        c.live[*p] = {it->first, dev};
+        c.cached -= it->first;
+        fl.erase(it);
+        return cudaSuccess;
+    }
+    e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {                       // out of memory: give the cached blocks back and retry once
+        cudaGetLastError();
+        tmp_drop_all_locked(c);
+        e = cudaMalloc(p, want);
+        if (e != cudaSuccess) return e;
+    }
+    c.live[*p] = {want, dev};
+    return cudaSuccess;
+}
+
+void tmp_free(void *p) {
+    if (!p) return;
+    TmpCache &c = tmpc();
+    std::lock_guard<std::mutex> g(c.mu);
+    auto it = c.live.find(p);
+    if (it == c.live.end()) { cudaFree(p); return; }          // not ours (defensive)
+    const size_t sz = it->second.first;
+    const int dev = it->second.second;
+    c.live.erase(it);
+    if (!c.cap_set) {
+        const char *e = getenv("CVXB_TMP_CACHE_MB");
+        c.cap = (size_t)(e ? atoll(e) : 4096) << 20;
+        c.cap_set = true;
+    }
+    if (sz > c.cap) { cudaFree(p); return; }
+    while (c.cached + sz > c.cap) {                           // evict the largest cached blocks first
+        size_t best = 0; int bd = -1;
+        for (int d = 0; d < 64; ++d)
+            if (!c.free_[d].empty() && c.free_[d].rbegin()->first >= best) { best = c.free_[d].rbegin()->first; bd = d; }
+        if (bd < 0) break;
+        auto last = std::prev(c.free_[bd].end());
+        int cur = 0; cudaGetDevice(&cur);
+        if (cur != bd) cudaSetDevice(bd);
+        cudaFree(last->second);
+        if (cur != bd) cudaSetDevice(cur);
+        c.cached -= last->first;
+        c.free_[bd].erase(last);
+    }
+    c.free_[dev & 63].emplace(sz, p);
+    c.cached += sz;
+}
+
+void tmp_cache_release() {
+    TmpCache &c = tmpc();
+    std::lock_guard<std::mutex> g(c.mu);
+    tmp_drop_all_locked(c);
+}
 
 void set_error(const char *fmt, ...) {
     char buf[1024];

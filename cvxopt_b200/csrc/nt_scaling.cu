@@ -10,8 +10,9 @@
 //                          Lz' Ls V = U lambda;  two GEMMs instead of a triangular solve), singular values sorted
 //                          descending as LAPACK's gesvd returns them (:398, :611).
 // The SVD replaces lapack.gesvd (src/C/lapack.c gesvd binding); blocks of order <= 48 run all sweeps inside one CTA
-// (shared memory), larger ones one launch per round of disjoint column pairs.
+// (shared memory), larger ones one cooperative launch per sweep (grid barrier between the rounds of disjoint column pairs).
 #include "cone.cuh"
+#include <cooperative_groups.h>
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
@@ -188,6 +189,51 @@ __global__ void __launch_bounds__(128) jacobi_round_kernel(int m, int m2, int r,
     if (threadIdx.x == 0) atomicAdd(nrot, 1);
 }
 
+// A whole sweep (all m2 - 1 rounds) in one cooperative launch: CTA t handles pair t of every round, a grid barrier
+// separates the rounds.  The per-round launches above cost ~25 us each at m = 512 (launch gap + three block
+// reductions + two passes over four columns); here a round is one fused reduction, the two passes and the barrier.
+__global__ void __launch_bounds__(128) jacobi_sweep_kernel(int m, int m2, double *B, double *V, int *nrot) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[3][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int rotated = 0;
+    for (int r = 0; r < m2 - 1; ++r) {
+        int p, q;
+        rr_pair(m2, r, blockIdx.x, p, q);
+        if (q < m) {
+            double *bp = B + (size_t)p * m, *bq = B + (size_t)q * m;
+            double a = 0.0, b = 0.0, g = 0.0;
+            for (int i = tid; i < m; i += 128) {
+                const double x = bp[i], y = bq[i];
+                a += x * x; b += y * y; g += x * y;
+            }
+            a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+            if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; sh[2][warp] = g; }
+            __syncthreads();
+            a = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+            b = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+            g = (sh[2][0] + sh[2][1]) + (sh[2][2] + sh[2][3]);
+            __syncthreads();
+            if ((fabs(g) > (2.0 * 2.220446049250313e-16 * sqrt((double)m)) * sqrt(a * b)) && g != 0.0) {
+                const double zeta = (b - a) / (2.0 * g);
+                const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + tt * tt), sn = c * tt;
+                double *vp = V + (size_t)p * m, *vq = V + (size_t)q * m;
+                for (int i = tid; i < m; i += 128) {
+                    const double x = bp[i], y = bq[i];
+                    bp[i] = c * x - sn * y; bq[i] = sn * x + c * y;
+                    const double u = vp[i], w = vq[i];
+                    vp[i] = c * u - sn * w; vq[i] = sn * u + c * w;
+                }
+                rotated = 1;
+            }
+        }
+        grid.sync();
+    }
+    if (rotated && tid == 0) atomicAdd(nrot, 1);
+}
+
 // Small blocks (m <= 48): the whole SVD iteration of one block inside one CTA, B and V in shared memory
 // (2 m^2 doubles <= 36 KB), one warp per column pair.
 __global__ void __launch_bounds__(256) jacobi_small_kernel(int m, double *Bg, double *Vg, int maxsweeps) {
@@ -286,9 +332,9 @@ NtCtx g_nt;
 
 struct DTemp {
     void *p = nullptr;
-    ~DTemp() { if (p) cudaFree(p); }
+    ~DTemp() { if (p) tmp_free(p); }
     int alloc(size_t bytes) {
-        CVXB_CUDA(cudaMalloc(&p, bytes ? bytes : 8));
+        CVXB_CUDA(tmp_malloc(&p, bytes ? bytes : 8));
         return 0;
     }
     double *d() const { return static_cast<double *>(p); }
@@ -320,11 +366,30 @@ int svd_jacobi(int m, double *B, double *Vw, double *U, double *V, double *sig, 
     set_identity_kernel<<<nb, T, 0, st>>>(m, Vw);
     count_launch();
     const int m2 = (m + 1) & ~1;
+    // one cooperative launch per sweep when every pair's CTA can be resident at once (CVXB_JACOBI_COOP=0: per-round launches)
+    bool coop = false;
+    {
+        static int coop_on = -1;
+        if (coop_on < 0) { const char *e = getenv("CVXB_JACOBI_COOP"); coop_on = (e && e[0] == '0') ? 0 : 1; }
+        int dev = 0, can = 0, per_sm = 0, sms = 0;
+        if (coop_on && cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && can &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_sweep_kernel, 128, 0) == cudaSuccess)
+            coop = (long long)per_sm * sms >= m2 / 2;
+    }
     for (int sweep = 0; sweep < 30; ++sweep) {
         CVXB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
-        for (int r = 0; r < m2 - 1; ++r) {
-            jacobi_round_kernel<<<m2 / 2, 128, 0, st>>>(m, m2, r, B, Vw, d_cnt);
+        if (coop) {
+            int mm_ = m, m2_ = m2;
+            void *args[] = {&mm_, &m2_, &B, &Vw, &d_cnt};
+            CVXB_CUDA(cudaLaunchCooperativeKernel((const void *)jacobi_sweep_kernel, dim3(m2 / 2), dim3(128), args, 0, st));
             count_launch();
+        } else {
+            for (int r = 0; r < m2 - 1; ++r) {
+                jacobi_round_kernel<<<m2 / 2, 128, 0, st>>>(m, m2, r, B, Vw, d_cnt);
+                count_launch();
+            }
         }
         CVXB_LAUNCH_CHECK();
         int cnt = 0;
@@ -359,11 +424,11 @@ int nt_ctx(NtCtx **out, std::unique_lock<std::mutex> &lk) {
 // stage host <-> device
 struct HBuf {
     double *dev = nullptr, *host = nullptr; size_t n = 0; bool owned = false;
-    ~HBuf() { if (owned && dev) cudaFree(dev); }
+    ~HBuf() { if (owned && dev) tmp_free(dev); }
     int in(double *src, size_t count, int space, cudaStream_t st, bool copy = true) {
         n = count; host = src;
         if (space == CVXB_DEVICE) { dev = src; return 0; }
-        CVXB_CUDA(cudaMalloc(&dev, (n ? n : 1) * sizeof(double)));
+        CVXB_CUDA(tmp_malloc(&dev, (n ? n : 1) * sizeof(double)));
         owned = true;
         if (n && copy) CVXB_CUDA(cudaMemcpyAsync(dev, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
         return 0;

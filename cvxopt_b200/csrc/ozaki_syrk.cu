@@ -2,8 +2,8 @@
 // accumulators in TMEM) by error-free slicing (Ozaki scheme).  kkt_api.cu uses it for the 'l'-row SYRK
 // of large problems (n >= 4096, ml >= 8192; CVXB_OZAKI=0 keeps the DMMA kernel, =2 forces it at any
 // size).  Replaces the same reference call as the DMMA SYRK: blas.syrk(Gs, K, trans='T') in
-// misc.kkt_chol.factor (misc.py:1275, blas.c:3039).  Measured: 18.5 ms at n=8192, m=16384 against
-// 33.7 ms on the fp64 DMMA pipe, result within 4e-16 * sum|terms| of an 80-bit evaluation.
+// misc.kkt_chol.factor (misc.py:1275, blas.c:3039).  Measured: 14.1 ms at n=8192, m=16384 (18.5 ms at the end of
+// round 1) against 33.7 ms on the fp64 DMMA pipe, result within 4e-16 * sum|terms| of an 80-bit evaluation.
 //
 // Arithmetic.  Column j of Gs = diag(d) A is written  Gs[k,j] = 2^e_j * sum_s q_s[k,j] 2^-(6+7s),
 // q_s integers in [-64, 64] (round-to-nearest digits, radix 2^7, e_j from the column maximum), so
@@ -18,7 +18,7 @@
 // reads: a "unit" is the 128-column x 32-row (K) block of one slice, 4 KB, K-major with the 32-byte
 // swizzle; units are ordered [column block][k step][slice] so that the first nS slices of one
 // (block, k step) are one contiguous bulk copy.  One CTA per 128x128 lower tile: warp 0 producer
-// (cp.async.bulk + mbarrier ring), warp 1 MMA issuer, warps 2-5 epilogue (TMEM -> fp64 -> C).
+// (cp.async.bulk + mbarrier ring), warp 1 MMA issuer, warps 2-9 epilogue (TMEM -> fp64 -> C).
 #include "common.cuh"
 #include <cstdint>
 #include <cstdlib>
@@ -902,10 +902,11 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     // flight form a compact block (few distinct operand streams -> L2 hits instead of HBM reads)
     // (rebuilt per call: a few microseconds, and no shared mutable state between threads / handles; the
     // pageable-source copy is staged before cudaMemcpyAsync returns)
-    // CVXB_OZ_2SM=1 selects the two-SM (cta_group::2) kernel.  Measured on B200 (profiles/r02c): correct, but a
-    // 256x128x32 int8 MMA issued for the SM pair takes 128 cycles (the pair runs at the rate of ONE SM's
-    // 128x128x32), so 21.5-24.8 ms against 18.5 ms for the one-SM kernel at n=8192, m=16384: off by default.
-    // CVXB_OZ_2SM=2 selects the WIDE two-SM kernel (256x256x32 MMAs, 256x256 blocks of C per SM pair).
+    // CVXB_OZ_2SM=1 selects the two-SM (cta_group::2) kernel, =2 its WIDE form (256x256x32 MMAs, 256x256 blocks of C
+    // per SM pair).  Both are correct and both are slower than the one-SM kernel (23.1 / 18.7 ms against 14.1 ms at
+    // n=8192, m=16384): not for the MMA rate (tools/int8_peak.cu: cta_group::2 256x128x32 = 64 cycles, 256x256x32 = 128)
+    // but for their copy pipeline -- every stage needs the peer's "full" relayed to the leader and a multicast commit
+    // back, and the ring holds 3 such stages; with MMAs disabled they still take 20-24 ms (profiles/r02p).  Opt-in.
     int two_sm = 0;
     if (const char *e = getenv("CVXB_OZ_2SM")) two_sm = (layout == 0 && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
     std::vector<unsigned int> order;

@@ -101,3 +101,36 @@ def test_distributed_entry_single_process_matches_qp_batch():
         np.testing.assert_allclose(got["x"], want["x"], rtol=1e-12, atol=1e-14)
         np.testing.assert_allclose(got["primal objective"], want["primal objective"], rtol=1e-12)
         assert set(tm) >= {"setup_ms", "scatter_ms", "solve_ms", "gather_ms"}
+
+
+def test_compaction_of_finished_problems(monkeypatch):
+    """The lock-step loop swaps finished problems out of the active prefix (csrc/batch_ipm.cu): per-problem results
+    are those of the uncompacted loop, come back in the caller's order, and a second solve on the same loaded batch
+    (slots restored first) repeats them."""
+    import cvxopt_b200
+    from cvxopt_b200.batch import QPBatch
+    B, n, m = 24, 40, 90
+    P, q, G, h = make_batch(B, n, m, seed0=500)
+    # mixed difficulty: scale some problems so that iteration counts differ
+    for k in range(0, B, 3):
+        q[k] *= 1e3
+        h[k] *= 1e-2
+    monkeypatch.setenv("CVXB_BATCH_COMPACT", "0")
+    plain = cvxopt_b200.qp_batch(P, q, G, h, nsub=1)
+    monkeypatch.setenv("CVXB_BATCH_COMPACT", "1")
+    b = QPBatch(B, n, m, 0)
+    try:
+        b.load(P, q, G, h)
+        b.solve()
+        r1 = b.results()
+        b.solve()
+        r2 = b.results()
+    finally:
+        b.close()
+    assert len(set(plain["iterations"])) > 1          # the test needs problems that finish at different iterations
+    for r in (r1, r2):
+        assert list(r["iterations"]) == list(plain["iterations"])
+        assert list(r["status_code"]) == list(plain["status_code"])
+        np.testing.assert_array_equal(r["x"], plain["x"])
+        np.testing.assert_array_equal(r["z"], plain["z"])
+        np.testing.assert_array_equal(r["primal objective"], plain["primal objective"])

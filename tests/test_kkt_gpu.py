@@ -295,7 +295,8 @@ def test_misc_solvers_mirror_ipm_side(dims):
 @pytest.mark.parametrize("dims", [{"l": 3, "q": [4], "s": [3, 8, 0, 1, 2]},      # one CTA per block (order <= 64)
                                   {"l": 0, "q": [], "s": [64, 33]},
                                   {"l": 2, "q": [], "s": [70, 5, 0, 1]},           # one launch per Jacobi round
-                                  {"l": 0, "q": [], "s": [129]}])
+                                  {"l": 0, "q": [], "s": [129]},
+                                  {"l": 1, "q": [], "s": [200, 130, 7]}])           # several CTAs per block and round
 def test_max_step_s_blocks_jacobi_eigensolver(dims):
     """max_step on 's' blocks (misc_solvers.c:1099-1150): smallest eigenvalue without sigma (dsyevr_),
     all eigenvalues + eigenvectors with sigma (dsyevd_ 'V').  Eigenvalues agree with LAPACK to
