@@ -387,6 +387,143 @@ potf2_inv_kernel(double *A, long long lda, int jb, double *inv, double *invT, in
     }
 }
 
+// ---- trailing update of the blocked factorisation:  A22(lower) -= L21 L21'  for one 128-wide panel ----
+// The generic DMMA GEMM runs this K = 128 update at 21-25 TF/s (57-67 % of the DMMA peak, profiles/r02v): every 128x64
+// tile is its own CTA with a pipeline prologue and an epilogue for only eight k steps.  Here a CTA (one per SM at a
+// time) walks a few consecutive 128x128 tiles strip by strip (strip = block column cb of the trailing matrix, rb >= cb):
+//   * the strip's column operand L21[cb rows, 0:128] (128 KB) stays in shared memory for all tiles of the strip;
+//   * the row operand streams through two 32-column buffers, the copy of the next chunk -- of the next TILE after
+//     the last chunk -- in flight under the DMMAs of the current one, so there is no per-tile prologue;
+//   * the tile of A22 goes straight into the accumulator fragments (acc = C, a-fragments negated: acc = C - L L')
+//     and is stored from them: no shared-memory staging, no epilogue barrier.
+// STATUS: validated correct (tests/test_kkt_gpu.py, tests/test_fullsize_gpu.py with CVXB_CHOL_TU=1) but SLOWER than the
+// generic kernel on B200 (17.6 vs 24 TF/s at the first step of n=8192: one 8-warp CTA per SM without register
+// double-buffering of the fragments and with the C tile's load/store latency exposed at every tile boundary does not
+// keep the DMMA pipe as busy as two 4-warp CTAs of the generic kernel do).  Opt-in: CVXB_CHOL_TU=1.
+// W = L21 (m x 128, column-major, ld ldw); tiles of block column 0 are left to the caller (the panel stream updates
+// the next block column itself).  Requires even ldc / 16-byte aligned C (the caller falls back to dmma_gemm otherwise).
+constexpr int TU_LD = NB + 4;                   // 132: row stride of the [k][idx] operand buffers (conflict-free LDS.64)
+constexpr int TU_CH = 32;                       // k columns per streamed chunk
+constexpr int TU_NCH = NB / TU_CH;
+constexpr int TU_SMEM = (NB * TU_LD + 2 * TU_CH * TU_LD) * 8;      // 202752 B
+
+__global__ void __launch_bounds__(256, 1)
+chol_trailing_kernel(int m, const double *__restrict__ W, long long ldw, double *C, long long ldc, int nbk, int cb0,
+                     long long T, unsigned long long *trace) {
+    extern __shared__ __align__(16) double sm[];
+    double *Bs = sm;                            // [128 k][TU_LD]  rows of block column cb
+    double *As = sm + NB * TU_LD;               // 2 x [32 k][TU_LD]  rows of block rb
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp & 1, wc = warp >> 1;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    if (trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicCAS(trace, 0ULL, t);
+    }
+    const long long t0 = T * blockIdx.x / gridDim.x, t1 = T * (blockIdx.x + 1) / gridDim.x;
+    if (t0 >= t1) return;
+    // tile t -> (cb, rb): strips cb = cb0 .. nbk-1, strip cb holds rb = cb .. nbk-1
+    int cb = cb0, rb;
+    {
+        long long t = t0;
+        while (t >= nbk - cb) { t -= nbk - cb; ++cb; }
+        rb = cb + (int)t;
+    }
+    auto issue_rows = [&](double *dst, int blk, int k0, int nk) {       // dst[kk][r] = W[blk*128 + r, k0 + kk]
+        for (int q = tid; q < nk * (NB / 2); q += 256) {
+            const int kk = q >> 6, rr = (q & 63) * 2;
+            const long long row = (long long)blk * NB + rr;
+            const int bytes = (row + 1 < m) ? 16 : (row < m ? 8 : 0);
+            cp_async16(dst + kk * TU_LD + rr, bytes ? W + row + (long long)(k0 + kk) * ldw : W, bytes);
+        }
+    };
+    int cur_cb = -1, buf = 0;
+    issue_rows(As, rb, 0, TU_CH);
+    cp_async_commit();
+    for (long long t = t0; t < t1; ++t) {
+        if (cb != cur_cb) {                     // new strip: every warp is past the previous tile's last barrier
+            issue_rows(Bs, cb, 0, NB);
+            cp_async_commit();
+            cur_cb = cb;
+        }
+        // ---- the tile of A22 -> accumulators ----
+        const long long r0 = (long long)rb * NB, c0 = (long long)cb * NB;
+        const bool interior = (rb > cb) && (r0 + NB <= m);
+        double acc[4][8][2];
+        double *Ct = C + r0 + c0 * ldc;
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) {
+            const int cl = wc * 32 + cf * 8 + g4;
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) {
+                const int rl = wr * 64 + rf * 8 + t4 * 2;
+                if (interior) {
+                    const double2 v = *reinterpret_cast<const double2 *>(Ct + rl + cl * ldc);
+                    acc[cf][rf][0] = v.x; acc[cf][rf][1] = v.y;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const long long r = r0 + rl + e, c = c0 + cl;
+                        acc[cf][rf][e] = (r < m && c < m && r >= c) ? Ct[rl + e + cl * ldc] : 0.0;
+                    }
+                }
+            }
+        }
+        // next tile (for the cross-tile prefetch)
+        int ncb = cb, nrb = rb + 1;
+        if (nrb >= nbk) { ++ncb; nrb = ncb; }
+        const bool has_next = (t + 1 < t1);
+#pragma unroll 1
+        for (int ch = 0; ch < TU_NCH; ++ch) {
+            if (ch + 1 < TU_NCH) issue_rows(As + (buf ^ 1) * TU_CH * TU_LD, rb, (ch + 1) * TU_CH, TU_CH);
+            else if (has_next) issue_rows(As + (buf ^ 1) * TU_CH * TU_LD, nrb, 0, TU_CH);
+            cp_async_commit();
+            cp_async_wait<1>();                 // everything but the chunk just issued has landed (incl. a new Bs)
+            __syncthreads();
+            const double *Ab = As + buf * TU_CH * TU_LD + (wr * 64 + g4) + t4 * TU_LD;
+            const double *Bb = Bs + (ch * TU_CH) * TU_LD + (wc * 32 + g4) + t4 * TU_LD;
+#pragma unroll
+            for (int kk = 0; kk < TU_CH / 4; ++kk) {
+                double a[4], bf[8];
+#pragma unroll
+                for (int cf = 0; cf < 4; ++cf) a[cf] = -Bb[cf * 8 + kk * 4 * TU_LD];
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) bf[rf] = Ab[rf * 8 + kk * 4 * TU_LD];
+#pragma unroll
+                for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+                    for (int rf = 0; rf < 8; ++rf) dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bf[rf]);
+            }
+            __syncthreads();                    // the buffer may be refilled by the next issue
+            buf ^= 1;
+        }
+        // ---- accumulators -> A22 ----
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) {
+            const int cl = wc * 32 + cf * 8 + g4;
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) {
+                const int rl = wr * 64 + rf * 8 + t4 * 2;
+                if (interior) {
+                    *reinterpret_cast<double2 *>(Ct + rl + cl * ldc) = make_double2(acc[cf][rf][0], acc[cf][rf][1]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const long long r = r0 + rl + e, c = c0 + cl;
+                        if (r < m && c < m && r >= c) Ct[rl + e + cl * ldc] = acc[cf][rf][e];
+                    }
+                }
+            }
+        }
+        cb = ncb; rb = nrb;
+    }
+    cp_async_wait<0>();
+    if (trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(trace + 1, t);
+    }
+}
+
 // ---- blocked triangular solve with one right-hand side ------------------------
 // forward:  L x = b ;  backward: L' x = b.   In place on b.  One CTA per 128-row block.
 // flags[i] == epoch  <=>  x_i is final in b.
@@ -570,6 +707,7 @@ int chol_work_create(CholWork &w) {
     CVXB_CUDA(cudaMalloc(&w.d_flags, 4096 * sizeof(int)));
     CVXB_CUDA(cudaMemset(w.d_flags, 0, 4096 * sizeof(int)));
     CVXB_CUDA(cudaMalloc(&w.splitk_ws, dmma_gemm_splitk_ws_doubles() * sizeof(double)));
+    CVXB_CUDA(cudaFuncSetAttribute(chol_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TU_SMEM));
     CVXB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    POTF2_SMEM));
     CVXB_CUDA(cudaFuncSetAttribute(trsv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
@@ -811,7 +949,31 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             u.alpha = -1.0; u.beta = 1.0; u.lower_only = true;
             u.ct_begin = odd ? 2 * panel_tiles : panel_tiles; u.ct_end = 1 << 30;
             u.trace = w.trace ? w.trace + 8 * jb + 6 : nullptr;
-            CVXB_TRY(dmma_gemm(u, U));
+            static int tu_on = -1;
+            // measured (profiles/r02x): correct, but ~35 us per 128x128 tile against 16.8 us of DMMA work -- potrf 12.0 ms
+            // with it, 10.5 ms without -- so it is an opt-in experiment (CVXB_CHOL_TU=1), the generic GEMM stays default
+            if (tu_on < 0) { const char *e = getenv("CVXB_CHOL_TU"); tu_on = (e && e[0] == '1') ? 1 : 0; }
+            const bool tu = tu_on && !odd && !pair && wj == NB && (lda & 1) == 0 && (ldw & 1) == 0 &&
+                            ((reinterpret_cast<uintptr_t>(A22) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Wp) & 15) == 0);
+            if (tu) {
+                // persistent strip kernel (chol_trailing_kernel): block columns 1 .. nbk-1 of the trailing matrix
+                const int nbk = (m + NB - 1) / NB;
+                const long long Tt = (long long)(nbk - 1) * nbk / 2;
+                if (Tt > 0) {
+                    // CTAs of ~3 tiles (~50 us): long enough to amortise the strip operand and the pipeline fill, short
+                    // enough that the SMs keep coming free for the chain / panel streams' kernels (a CTA of this
+                    // kernel fills an SM's shared memory: nothing else can be resident beside it)
+                    static int tpc = -1;
+                    if (tpc < 0) { const char *e = getenv("CVXB_CHOL_TU_TILES"); tpc = e ? std::max(1, atoi(e)) : 3; }
+                    const long long waves = (Tt + (long long)kNumSMs * tpc - 1) / ((long long)kNumSMs * tpc);
+                    const int grid = (int)std::min<long long>(Tt, waves * kNumSMs);
+                    chol_trailing_kernel<<<grid, 256, TU_SMEM, U>>>(m, Wp, ldw, A22, lda, nbk, 1, Tt, u.trace);
+                    count_launch();
+                    CVXB_LAUNCH_CHECK();
+                }
+            } else {
+                CVXB_TRY(dmma_gemm(u, U));
+            }
             CVXB_CUDA(cudaEventRecord(w.ev_r[jb], U));
             prev_r = last_r;
             last_r = jb;
