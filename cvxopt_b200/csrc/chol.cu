@@ -524,6 +524,140 @@ chol_trailing_kernel(int m, const double *__restrict__ W, long long ldw, double 
     }
 }
 
+// Second form of the strip kernel (CVXB_CHOL_TU=2; validated, also slower: potrf 11.8 ms, profiles/r02x): the generic GEMM's geometry -- 128x64 tiles, four warps, two CTAs per
+// SM so that one CTA's tile boundary (store C, load the next C into the accumulators) runs under the other's DMMAs --
+// but a CTA walks several consecutive tiles of a 64-column strip and its 3-stage operand ring never drains: the chunks
+// of the next tile follow the last chunk of the current one.
+constexpr int T2_BC = 64, T2_LDA = NB + 4, T2_LDB = T2_BC + 4, T2_CH = 16, T2_ST = 3;
+constexpr int T2_STAGE = T2_CH * (T2_LDA + T2_LDB);            // doubles per stage: A chunk then B chunk
+constexpr int T2_SMEM = T2_ST * T2_STAGE * 8;                  // 76800 B
+constexpr int T2_NCH = NB / T2_CH;                             // 8 chunks per tile
+
+__global__ void __launch_bounds__(128, 2)
+chol_trailing2_kernel(int m, const double *__restrict__ W, long long ldw, double *C, long long ldc, int nbk, long long T,
+                      unsigned long long *trace) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp & 1, wc = warp >> 1;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    if (trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicCAS(trace, 0ULL, t);
+    }
+    const long long t0 = T * blockIdx.x / gridDim.x, t1 = T * (blockIdx.x + 1) / gridDim.x;
+    if (t0 >= t1) return;
+    // tile t -> (cs, rb): 64-column strips cs = 2 .. 2*nbk-1 (the first 128 columns belong to the panel stream),
+    // strip cs holds the 128-row blocks rb = cs/2 .. nbk-1
+    int cs = 2, rb;
+    {
+        long long t = t0;
+        while (t >= nbk - (cs >> 1)) { t -= nbk - (cs >> 1); ++cs; }
+        rb = (cs >> 1) + (int)t;
+    }
+    auto issue = [&](int stage, int rblk, int cstrip, int k0) {
+        double *As = sm + stage * T2_STAGE, *Bs = As + T2_CH * T2_LDA;
+        for (int q = tid; q < T2_CH * (NB / 2); q += 128) {           // A: rows of block rblk
+            const int kk = q >> 6, rr = (q & 63) * 2;
+            const long long row = (long long)rblk * NB + rr;
+            const int bytes = (row + 1 < m) ? 16 : (row < m ? 8 : 0);
+            cp_async16(As + kk * T2_LDA + rr, bytes ? W + row + (long long)(k0 + kk) * ldw : W, bytes);
+        }
+        for (int q = tid; q < T2_CH * (T2_BC / 2); q += 128) {        // B: rows of strip cstrip
+            const int kk = q >> 5, rr = (q & 31) * 2;
+            const long long row = (long long)cstrip * T2_BC + rr;
+            const int bytes = (row + 1 < m) ? 16 : (row < m ? 8 : 0);
+            cp_async16(Bs + kk * T2_LDB + rr, bytes ? W + row + (long long)(k0 + kk) * ldw : W, bytes);
+        }
+    };
+    // the chunk stream of this CTA: chunk q of tile i; `pf_*` walks two chunks ahead of the compute position
+    int pf_cs = cs, pf_rb = rb, pf_ch = 0;
+    long long pf_t = t0;
+    int pf_stage = 0;
+    auto prefetch = [&]() {
+        if (pf_t < t1) {
+            issue(pf_stage, pf_rb, pf_cs, pf_ch * T2_CH);
+            if (++pf_ch == T2_NCH) {
+                pf_ch = 0; ++pf_t;
+                if (++pf_rb >= nbk) { ++pf_cs; pf_rb = pf_cs >> 1; }
+            }
+        }
+        cp_async_commit();
+        if (++pf_stage == T2_ST) pf_stage = 0;
+    };
+    prefetch();
+    prefetch();
+    int stage = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const long long r0 = (long long)rb * NB, c0 = (long long)cs * T2_BC;
+        const bool interior = (r0 >= c0 + T2_BC) && (r0 + NB <= m);
+        double acc[4][8][2];
+        double *Ct = C + r0 + c0 * ldc;
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) {
+            const int cl = wc * 32 + cf * 8 + g4;
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) {
+                const int rl = wr * 64 + rf * 8 + t4 * 2;
+                if (interior) {
+                    const double2 v = *reinterpret_cast<const double2 *>(Ct + rl + cl * ldc);
+                    acc[cf][rf][0] = v.x; acc[cf][rf][1] = v.y;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const long long r = r0 + rl + e, c = c0 + cl;
+                        acc[cf][rf][e] = (r < m && c < m && r >= c) ? Ct[rl + e + cl * ldc] : 0.0;
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < T2_NCH; ++ch) {
+            cp_async_wait<T2_ST - 2>();         // this chunk has landed (one newer group may be in flight)
+            __syncthreads();                    // ... for every thread; the stage read last iteration is free
+            prefetch();                         // two chunks ahead, into the stage freed by the barrier above
+            const double *As = sm + stage * T2_STAGE, *Bs = As + T2_CH * T2_LDA;
+            const double *Ab = As + (wr * 64 + g4) + t4 * T2_LDA;
+            const double *Bb = Bs + (wc * 32 + g4) + t4 * T2_LDB;
+#pragma unroll
+            for (int kk = 0; kk < T2_CH / 4; ++kk) {
+                double a[4], bf[8];
+#pragma unroll
+                for (int cf = 0; cf < 4; ++cf) a[cf] = -Bb[cf * 8 + kk * 4 * T2_LDB];
+#pragma unroll
+                for (int rf = 0; rf < 8; ++rf) bf[rf] = Ab[rf * 8 + kk * 4 * T2_LDA];
+#pragma unroll
+                for (int cf = 0; cf < 4; ++cf)
+#pragma unroll
+                    for (int rf = 0; rf < 8; ++rf) dmma(acc[cf][rf][0], acc[cf][rf][1], a[cf], bf[rf]);
+            }
+            if (++stage == T2_ST) stage = 0;
+        }
+#pragma unroll
+        for (int cf = 0; cf < 4; ++cf) {
+            const int cl = wc * 32 + cf * 8 + g4;
+#pragma unroll
+            for (int rf = 0; rf < 8; ++rf) {
+                const int rl = wr * 64 + rf * 8 + t4 * 2;
+                if (interior) {
+                    *reinterpret_cast<double2 *>(Ct + rl + cl * ldc) = make_double2(acc[cf][rf][0], acc[cf][rf][1]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const long long r = r0 + rl + e, c = c0 + cl;
+                        if (r < m && c < m && r >= c) Ct[rl + e + cl * ldc] = acc[cf][rf][e];
+                    }
+                }
+            }
+        }
+        if (++rb >= nbk) { ++cs; rb = cs >> 1; }
+    }
+    cp_async_wait<0>();
+    if (trace && tid == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(trace + 1, t);
+    }
+}
+
 // ---- blocked triangular solve with one right-hand side ------------------------
 // forward:  L x = b ;  backward: L' x = b.   In place on b.  One CTA per 128-row block.
 // flags[i] == epoch  <=>  x_i is final in b.
@@ -708,6 +842,7 @@ int chol_work_create(CholWork &w) {
     CVXB_CUDA(cudaMemset(w.d_flags, 0, 4096 * sizeof(int)));
     CVXB_CUDA(cudaMalloc(&w.splitk_ws, dmma_gemm_splitk_ws_doubles() * sizeof(double)));
     CVXB_CUDA(cudaFuncSetAttribute(chol_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TU_SMEM));
+    CVXB_CUDA(cudaFuncSetAttribute(chol_trailing2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
     CVXB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    POTF2_SMEM));
     CVXB_CUDA(cudaFuncSetAttribute(trsv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
@@ -952,14 +1087,28 @@ static int potrf_enqueue(int n, double *A, int lda, double *inv, CholWork &w, cu
             static int tu_on = -1;
             // measured (profiles/r02x): correct, but ~35 us per 128x128 tile against 16.8 us of DMMA work -- potrf 12.0 ms
             // with it, 10.5 ms without -- so it is an opt-in experiment (CVXB_CHOL_TU=1), the generic GEMM stays default
-            if (tu_on < 0) { const char *e = getenv("CVXB_CHOL_TU"); tu_on = (e && e[0] == '1') ? 1 : 0; }
+            if (tu_on < 0) { const char *e = getenv("CVXB_CHOL_TU"); tu_on = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }
             const bool tu = tu_on && !odd && !pair && wj == NB && (lda & 1) == 0 && (ldw & 1) == 0 &&
                             ((reinterpret_cast<uintptr_t>(A22) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Wp) & 15) == 0);
             if (tu) {
                 // persistent strip kernel (chol_trailing_kernel): block columns 1 .. nbk-1 of the trailing matrix
                 const int nbk = (m + NB - 1) / NB;
                 const long long Tt = (long long)(nbk - 1) * nbk / 2;
-                if (Tt > 0) {
+                if (tu_on == 2) {
+                    // 128 x 64 tiles, two CTAs per SM, ~6 tiles (~3 of the 128 x 128 ones) per CTA
+                    long long T2 = 0;
+                    for (int c2 = 2; c2 < 2 * nbk; ++c2) T2 += nbk - (c2 >> 1);
+                    if (T2 > 0) {
+                        static int tpc2 = -1;
+                        if (tpc2 < 0) { const char *e = getenv("CVXB_CHOL_TU_TILES"); tpc2 = e ? std::max(1, atoi(e)) : 6; }
+                        const long long slots = 2LL * kNumSMs;
+                        const long long waves = (T2 + slots * tpc2 - 1) / (slots * tpc2);
+                        const int grid = (int)std::min<long long>(T2, waves * slots);
+                        chol_trailing2_kernel<<<grid, 128, T2_SMEM, U>>>(m, Wp, ldw, A22, lda, nbk, T2, u.trace);
+                        count_launch();
+                        CVXB_LAUNCH_CHECK();
+                    }
+                } else if (Tt > 0) {
                     // CTAs of ~3 tiles (~50 us): long enough to amortise the strip operand and the pipeline fill, short
                     // enough that the SMs keep coming free for the chain / panel streams' kernels (a CTA of this
                     // kernel fills an SM's shared memory: nothing else can be resident beside it)
