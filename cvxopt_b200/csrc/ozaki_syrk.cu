@@ -809,9 +809,13 @@ __global__ void __launch_bounds__(OZ_T) oz_slice_kernel(int m, int n, const doub
 #pragma unroll
             for (int s = 0; s < OZ_SMAX; ++s) {
                 if (s < S) {
-                    const double q = rint(x);
+                    // round to nearest-even integer by adding 1.5 * 2^52 (|x| <= 8192 here): the sum's low mantissa word
+                    // IS the integer in two's complement, so there is neither a FRND nor an F2I (both quarter rate) per
+                    // digit: this kernel was bound by them (0.71 ms for 2.3 GB of traffic)
+                    const double t = x + 6755399441055744.0;
+                    const double q = t - 6755399441055744.0;               // == rint(x)
                     x = (x - q) * 128.0;                                   // exact
-                    pk[s][e >> 2] |= ((uint32_t)(int)q & 0xFFu) << ((e & 3) * 8);
+                    pk[s][e >> 2] |= ((uint32_t)__double2loint(t) & 0xFFu) << ((e & 3) * 8);
                 }
             }
         }
