@@ -125,8 +125,9 @@ def run_batch_distributed(nprob, n, m, rank, world, dev):
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
     keys = ("scatter_ms", "solve_ms", "gather_ms")
-    t = torch.tensor([tm[k] for k in keys] + [sum(tm[k] for k in keys), res.get("solve_ms", 0.0), wall],
-                     dtype=torch.float64, device=dev)
+    sub = ("solve_load_wall_ms", "solve_ipm_wall_ms", "solve_collect_wall_ms")
+    t = torch.tensor([tm[k] for k in keys] + [sum(tm[k] for k in keys), res.get("solve_ms", 0.0), wall] +
+                     [tm.get(k, 0.0) for k in sub], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank != 0:
@@ -139,6 +140,8 @@ def run_batch_distributed(nprob, n, m, rank, world, dev):
                         "(interleaved shards) -> NCCL gather" % (nprob, n, m, world),
             "scatter_ms": float(t[0].item()), "solve_ms": float(t[1].item()), "gather_ms": float(t[2].item()),
             "ms": total, "ipm_kernel_ms": float(t[4].item()), "wall_ms_incl_h2d_of_batch": float(t[5].item()),
+            "solve_phase_wall_ms": {"load_shards_into_subbatches": float(t[6].item()), "ipm": float(t[7].item()),
+                                    "collect_results": float(t[8].item())},
             "timing": "device events per phase, max over ranks; ms = scatter + solve + gather; the one-off H2D of "
                       "the 3.2 GB batch on rank 0 is outside (wall_ms includes it)",
             "scattered_bytes": int(8 * (nprob - len(res["indices"])) * (n * n + n + m * n + m)),

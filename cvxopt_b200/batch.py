@@ -353,9 +353,14 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
                     # stream) must be complete before it reads them
                     torch.cuda.current_stream().synchronize()
                     part.load_ptr(sl[0].data_ptr(), sl[1].data_ptr(), sl[2].data_ptr(), sl[3].data_ptr(), _lib.DEVICE)
+                tw = time.perf_counter()
                 b.load_ptr_sliced(loader)
                 del keepalive
+                clk.t["solve_load_wall_ms"] = (time.perf_counter() - tw) * 1e3
+                tw = time.perf_counter()
                 b.solve(**options)
+                clk.t["solve_ipm_wall_ms"] = (time.perf_counter() - tw) * 1e3
+                tw = time.perf_counter()
                 for ix, part in zip(b.idx, b.parts):
                     kk = len(ix)
                     it = torch.from_numpy(ix).to(dev)
@@ -374,6 +379,8 @@ def qp_batch_distributed(P, q, G, h, solver=None, group=None, sharding="interlea
                     sc.index_copy_(0, it, torch.from_numpy(np.stack(
                         [status.astype(np.float64), iters.astype(np.float64), pobj, dobj], axis=1)).to(dev))
                 stats = b.stats()
+                torch.cuda.synchronize()
+                clk.t["solve_collect_wall_ms"] = (time.perf_counter() - tw) * 1e3
             except BaseException:
                 b.close()
                 raise
