@@ -53,6 +53,7 @@ _SIGS = {
     "cvxb_kkt_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
     "cvxb_kkt_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "cvxb_kkt_last_breakdown": (C.c_int, [C.c_void_p, c_double_p]),
+    "cvxb_kkt_syrk_mma_ms": (C.c_int, [C.c_void_p, c_double_p]),
     "cvxb_kkt_syrk_path": (C.c_int, [C.c_void_p]),
     "cvxb_kkt_qr_passes": (C.c_int, [C.c_void_p]),
     "cvxb_kkt_gemv_G": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,

@@ -142,6 +142,7 @@ int dmma_gemm_tile_cols();              // width of a c tile (units of ct_begin 
 
 // ozaki_syrk.cu (experimental): C(lower) = A' diag(d)^2 A + beta*D through int8 slices on tcgen05
 size_t ozaki_workspace_bytes(int n, int m, int S);
+void ozaki_time_mma(cudaEvent_t a, cudaEvent_t b);   // events recorded around the MMA launches of this thread's next call
 int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, const double *D,
                long long ldd, double beta, double *C, long long ldc, int S, int layout, void *work,
                unsigned int *dbg, cudaStream_t st);

@@ -292,6 +292,7 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     KCUDA(cudaEventCreate(&k->e0)); KCUDA(cudaEventCreate(&k->e1));
     KCUDA(cudaEventCreate(&k->e2)); KCUDA(cudaEventCreate(&k->e3));
     KCUDA(cudaEventCreate(&k->t0)); KCUDA(cudaEventCreate(&k->t1));
+    KCUDA(cudaEventCreate(&k->m0)); KCUDA(cudaEventCreate(&k->m1));
     KTRY(chol_work_create(k->cw));
     const size_t nn = (size_t)(n > 0 ? n : 1);
     if (space == CVXB_DEVICE) {
@@ -369,7 +370,7 @@ void cvxb_kkt_destroy(cvxb_kkt *k) {
     k->W.destroy();
     k->cone.destroy();
     chol_work_destroy(k->cw);
-    cudaEvent_t evs[] = {k->e0, k->e1, k->e2, k->e3, k->t0, k->t1};
+    cudaEvent_t evs[] = {k->e0, k->e1, k->e2, k->e3, k->t0, k->t1, k->m0, k->m1};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     if (k->st) cudaStreamDestroy(k->st);
     delete k;
@@ -491,6 +492,7 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
         k->syrk_path = 0;
         if (c.ml > 0 && n > 0 && i8) {
             // G_l' diag(di)^2 G_l + H from nine int8 slices per entry (exact products, fp64-level result)
+            ozaki_time_mma(k->m0, k->m1);
             CVXB_TRY(ozaki_syrk(n, c.ml, k->G + c.mnl, k->ldg, k->W.di, Hptr, ldH, 1.0, k->Kmat, ldk, 9, 0,
                                 k->oz_work, nullptr, st));
             have = true;
@@ -581,6 +583,9 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
     cudaEventElapsedTime(&t, k->e0, k->e1); k->br[0] = t;
     cudaEventElapsedTime(&t, k->e1, k->e2); k->br[1] = t;
     cudaEventElapsedTime(&t, k->e2, k->e3); k->br[2] = t;
+    k->mma_ms = 0.0;
+    if (k->syrk_path == 2 && k->method == 0 && cudaEventElapsedTime(&t, k->m0, k->m1) == cudaSuccess) k->mma_ms = t;
+    cudaGetLastError();
     if (info > 0) {
         set_error("factor: leading minor of order %d is not positive definite", info);
         return info;
@@ -699,6 +704,12 @@ int cvxb_kkt_qr_passes(cvxb_kkt *k) { return (k && k->method == 1) ? kkt_qr_pass
 int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3) {
     if (!k || !ms3) return CVXB_E_ARG;
     ms3[0] = k->br[1]; ms3[1] = k->br[2]; ms3[2] = k->br[0];
+    return 0;
+}
+
+int cvxb_kkt_syrk_mma_ms(cvxb_kkt *k, double *ms) {
+    if (!k || !ms) return CVXB_E_ARG;
+    *ms = k->mma_ms;
     return 0;
 }
 

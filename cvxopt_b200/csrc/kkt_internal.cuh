@@ -42,6 +42,8 @@ struct cvxb_kkt {
     CholWork cw;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr, t0 = nullptr, t1 = nullptr;
+    cudaEvent_t m0 = nullptr, m1 = nullptr;      // around the MMA launches of the int8-slice SYRK
+    double mma_ms = 0.0;
     double factor_ms = 0, solve_ms = 0, br[3] = {0, 0, 0};
     bool factored = false;
     // SYRK of the 'l' rows on the int8 tensor path (ozaki_syrk.cu): 0 off (DMMA kernel), 1 for large

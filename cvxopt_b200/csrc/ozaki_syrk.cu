@@ -876,6 +876,11 @@ static void oz_choose_groups(int S, int *npass, int *pd0, int *pd1) {
     *npass = bestn;
 }
 
+// Optional timing of the MMA launches alone (without the two slicing kernels): the NEXT ozaki_syrk call of this thread
+// records `a` before its first MMA launch and `b` after its last one (bench.py's roofline line via cvxb_kkt_syrk_mma_ms).
+static thread_local cudaEvent_t g_oz_ev0 = nullptr, g_oz_ev1 = nullptr;
+void ozaki_time_mma(cudaEvent_t a, cudaEvent_t b) { g_oz_ev0 = a; g_oz_ev1 = b; }
+
 size_t ozaki_workspace_bytes(int n, int m, int S) {
     const size_t nblk = (n + OZ_T - 1) / OZ_T, nk = std::max(1, (m + OZ_KS - 1) / OZ_KS);
     return nblk * nk * (size_t)S * OZ_UNIT + 2 * (size_t)n * sizeof(double) + nblk * (nblk + 1) / 2 * sizeof(unsigned int) + 1024
@@ -983,6 +988,9 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
     }
     if (const char *e = getenv("CVXB_OZ_ABLATE")) p.ablate = atoi(e);
     oz_choose_groups(S, &p.npass, p.pd0, p.pd1);
+    cudaEvent_t tev0 = g_oz_ev0, tev1 = g_oz_ev1;
+    g_oz_ev0 = g_oz_ev1 = nullptr;
+    if (tev0) CVXB_CUDA(cudaEventRecord(tev0, st));
     long long t1_first = 0, t1_count = tiles;            // 128 x 128 tiles left to the one-SM kernel
     if (two_sm) {
         OzParams p2 = p;
@@ -1032,6 +1040,7 @@ int ozaki_syrk(int n, int m, const double *A, long long lda, const double *d, co
             count_launch(2);
         }
     }
+    if (tev1) CVXB_CUDA(cudaEventRecord(tev1, st));
     count_launch();
     CVXB_LAUNCH_CHECK();
     return 0;

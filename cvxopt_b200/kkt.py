@@ -272,7 +272,12 @@ class KKTChol:
     def last_breakdown(self):
         b = (C.c_double * 3)()
         self._lib.cvxb_kkt_last_breakdown(self._h, b)
-        return {"syrk_ms": b[0], "potrf_ms": b[1], "scale_ms": b[2]}
+        out = {"syrk_ms": b[0], "potrf_ms": b[1], "scale_ms": b[2]}
+        mm = C.c_double()
+        self._lib.cvxb_kkt_syrk_mma_ms(self._h, C.byref(mm))
+        if mm.value > 0:
+            out["syrk_mma_ms"] = mm.value        # int8-slice path: the MMA launches alone (without slicing kernels)
+        return out
 
     def syrk_path(self):
         """'none' | 'dmma' | 'int8': the kernel that computed the last factor's 'l'-row SYRK"""

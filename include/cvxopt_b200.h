@@ -130,6 +130,9 @@ int cvxb_kkt_last_breakdown(cvxb_kkt *k, double *ms3);
  * (mma.sync.m8n8k4.f64), 2 int8 slices on tcgen05.mma kind::i8 (large problems; CVXB_OZAKI=0 disables,
  * falls back to 1 when the slice workspace does not fit in device memory) */
 int cvxb_kkt_syrk_path(cvxb_kkt *k);
+/* int8-slice path only: CUDA-event time of the MMA launches of the last factor's SYRK, without the two slicing kernels
+ * (0 on the DMMA path); bench.py's roofline line divides the int8 operations by this */
+int cvxb_kkt_syrk_mma_ms(cvxb_kkt *k, double *ms);
 /* QR route: Cholesky-QR passes of the last factor: 2 (plain, re-orthogonalised) or 3 (shifted, ill-conditioned) */
 int cvxb_kkt_qr_passes(cvxb_kkt *k);
 
