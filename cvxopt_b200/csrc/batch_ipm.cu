@@ -348,7 +348,9 @@ int batch_factor(cvxb_batch *b) {
         if (need > b->oz_bytes) {
             if (b->oz_work) cudaFree(b->oz_work);
             b->oz_work = nullptr; b->oz_bytes = 0;
-            if (cudaMalloc(&b->oz_work, need) != cudaSuccess) {
+            cudaError_t ae = cudaMalloc(&b->oz_work, need);
+            if (ae == cudaErrorMemoryAllocation) { cudaGetLastError(); tmp_cache_release(); ae = cudaMalloc(&b->oz_work, need); }
+            if (ae != cudaSuccess) {
                 cudaGetLastError();
                 b->oz_work = nullptr;
                 i8 = false;
@@ -424,7 +426,10 @@ int cvxb_batch_create(cvxb_batch **out, int nprob, int n, int m, int device) {
     b->nblk = (n + NB - 1) / NB;
     b->sInv = (long long)2 * b->nblk * NB * NB;
     auto fail = [&](int r) { cvxb_batch_destroy(b); return r; };
-#define BCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+#define BCUDA(expr) do { cudaError_t _e = (expr); \
+        /* out of memory: give the scratch-buffer cache (common.cuh) back to the driver and try once more */ \
+        if (_e == cudaErrorMemoryAllocation) { cudaGetLastError(); tmp_cache_release(); _e = (expr); } \
+        if (_e != cudaSuccess) { \
         set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
         return fail(_e == cudaErrorMemoryAllocation ? CVXB_E_NOMEM : CVXB_E_CUDA); } } while (0)
     const size_t B = nprob;

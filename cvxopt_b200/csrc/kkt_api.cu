@@ -285,7 +285,10 @@ int cvxb_kkt_create(cvxb_kkt **out, int n, int p, const cvxb_dims *dims, const d
     }
     auto fail = [&](int r) { cvxb_kkt_destroy(k); return r; };
 #define KTRY(expr) do { int _r = (expr); if (_r) return fail(_r); } while (0)
-#define KCUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+#define KCUDA(expr) do { cudaError_t _e = (expr); \
+        /* out of memory: give the scratch-buffer cache (common.cuh) back to the driver and try once more */ \
+        if (_e == cudaErrorMemoryAllocation) { cudaGetLastError(); tmp_cache_release(); _e = (expr); } \
+        if (_e != cudaSuccess) { \
         set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
         return fail(_e == cudaErrorMemoryAllocation ? CVXB_E_NOMEM : CVXB_E_CUDA); } } while (0)
     KCUDA(cudaStreamCreateWithFlags(&k->st, cudaStreamNonBlocking));
@@ -480,7 +483,9 @@ int cvxb_kkt_factor(cvxb_kkt *k, const cvxb_scaling *Wp, const double *H, int ld
             if (need > k->oz_bytes) {
                 if (k->oz_work) cudaFree(k->oz_work);
                 k->oz_work = nullptr; k->oz_bytes = 0;
-                if (cudaMalloc(&k->oz_work, need) != cudaSuccess) {
+                cudaError_t ae = cudaMalloc(&k->oz_work, need);
+                if (ae == cudaErrorMemoryAllocation) { cudaGetLastError(); tmp_cache_release(); ae = cudaMalloc(&k->oz_work, need); }
+                if (ae != cudaSuccess) {
                     cudaGetLastError();
                     k->oz_work = nullptr;
                     i8 = false;
