@@ -67,7 +67,9 @@ def test_device_conelp_on_configs_3_and_5(name, n, dims):
     # functions.  Through the plugin boundary (the reference's own driver arithmetic) the count is exact
     # (tests/test_fullsize_gpu.py).
     assert abs(got["iterations"] - b["iterations"]) <= 1
-    np.testing.assert_allclose(got["primal objective"], b["primal objective"], rtol=1e-8)
-    # the duality gap at termination is within reltol = 1e-6 of the objective; one iteration more or less moves the
-    # dual objective inside that gap
-    np.testing.assert_allclose(got["dual objective"], b["dual objective"], rtol=1e-6)
+    # Same iteration count: the iterates are the reference's (1e-8).  One iteration more or less: both final iterates
+    # are optimal to the stopping rule, their objectives differ by what remains of the gap (reltol = 1e-6 of the
+    # objective for the dual, measured 5.6e-9 for the primal on config 3).
+    same = got["iterations"] == b["iterations"]
+    np.testing.assert_allclose(got["primal objective"], b["primal objective"], rtol=1e-8 if same else 1e-7)
+    np.testing.assert_allclose(got["dual objective"], b["dual objective"], rtol=1e-7 if same else 1e-6)
